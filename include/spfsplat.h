@@ -1,0 +1,165 @@
+/* spfsplat.h -- C ABI of libspfsplat.so (sm_100a), the B200-native replacement for the two
+ * native components on SPFSplatV2's decoder hot path:
+ *
+ *   (1) the external `diff_gauss_pose` rasterizer that
+ *       /root/reference/src/model/decoder/cuda_splatting.py:5,105-138,218-249 constructs and calls
+ *       once per view (GaussianRasterizationSettings + GaussianRasterizer.__call__), and
+ *   (2) the in-tree `curope` extension, entry `rope_2d(tokens, positions, base, fwd)`
+ *       (/root/reference/src/model/encoder/backbone/croco/curope/curope.cpp:49-69, kernels.cu:84-108).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller (torch caching allocator).  The library
+ *     never allocates, frees or retains memory, keeps no mutable global state (re-entrant; forward and
+ *     backward may come from different host threads), launches only on the stream it is given and
+ *     never synchronises the device.
+ *   - Return value: 0 = ok, negative = SpfStatus.  spf_last_error() returns a thread-local message.
+ *   - Matrices are row-major 4x4 in the ROW-VECTOR convention the reference passes (transposed
+ *     world->camera and projection, cuda_splatting.py:88-90): p_view = [m,1] * viewmatrix.
+ *   - A call renders B = n_scenes * views_per_scene views; view i reads the Gaussians of scene
+ *     i / views_per_scene (this replaces the v-fold `repeat` copies of
+ *     /root/reference/src/model/decoder/decoder_splatting_cuda.py:58-64).
+ */
+#ifndef SPFSPLAT_H_
+#define SPFSPLAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SPF_API __attribute__((visibility("default")))
+#else
+#define SPF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SPF_OK = 0,
+  SPF_ERR_BAD_ARG = -1,        /* null pointer, bad size / degree / alignment */
+  SPF_ERR_WORKSPACE = -2,      /* a caller-provided buffer is too small */
+  SPF_ERR_CUDA = -3,           /* a CUDA runtime call or launch failed (message has the code) */
+  SPF_ERR_UNSUPPORTED = -4
+} SpfStatus;
+
+enum {
+  SPF_FLAG_SH_LAYOUT_CK = 1u << 0, /* sh is [S,P,3,K] (the encoder's native `harmonics` layout,
+                                      /root/reference/src/model/types.py:13) instead of [S,P,K,3]
+                                      (what cuda_splatting.py:79 materialises) */
+  SPF_FLAG_NO_COV_GRAD  = 1u << 1, /* settings.enable_cov_grad == False */
+  SPF_FLAG_NO_SH_GRAD   = 1u << 2, /* settings.enable_sh_grad == False */
+  SPF_FLAG_NO_TMA       = 1u << 3, /* debugging: stage the slab with plain loads instead of cp.async.bulk */
+  SPF_FLAG_QUAT_XYZW    = 1u << 4, /* rotations are (x,y,z,w); default (w,x,y,z) */
+  SPF_FLAG_DEPTH_NORMALIZED = 1u << 5 /* reserved (depth / alpha); not implemented */
+};
+
+/* Problem description; mirrors GaussianRasterizationSettings (cuda_splatting.py:105-120). */
+typedef struct {
+  int32_t n_scenes;          /* S */
+  int32_t views_per_scene;   /* v ;  B = S*v */
+  int32_t n_gaussians;       /* P per scene */
+  int32_t image_height;      /* settings.image_height */
+  int32_t image_width;       /* settings.image_width  */
+  int32_t sh_degree;         /* settings.sh_degree, 0..4; ignored when colors_precomp is used */
+  uint32_t flags;            /* SPF_FLAG_* */
+  float   scale_modifier;    /* settings.scale_modifier */
+  int64_t dup_capacity;      /* capacity (records) of bucket / slab / dup_grad buffers */
+} SpfRasterDesc;
+
+/* Inputs (forward kwargs of GaussianRasterizer.__call__, cuda_splatting.py:128-138, batched). */
+typedef struct {
+  const float* means3D;      /* [S,P,3] */
+  const float* scales;       /* [S,P,3] */
+  const float* rotations;    /* [S,P,4] */
+  const float* opacities;    /* [S,P]   */
+  const float* shs;          /* [S,P,K,3] or [S,P,3,K]; NULL if colors_precomp */
+  const float* colors_precomp; /* [S,P,3] or NULL */
+  int32_t      sh_coeffs;    /* K stored per channel in `shs` (>= (sh_degree+1)^2) */
+  const float* viewmatrix;   /* [B,16] */
+  const float* projmatrix;   /* [B,16]  settings.projmatrix */
+  const float* tanfov;       /* [B,2]   settings.tanfovx, tanfovy */
+  const float* bg;           /* [B,3]   settings.bg */
+  const float* pre_scale;    /* [B] or NULL: means and scales are multiplied by this before use
+                                (the 1/near scale-invariance step, cuda_splatting.py:66-74) */
+} SpfRasterIn;
+
+/* Caller-allocated intermediates.  Forward fills them; backward reads them.
+ * T = ceil(W/16)*ceil(H/16) tiles per view, NB = ceil(P/128) projection blocks per view. */
+typedef struct {
+  float*    xy;              /* [B,P,2]  projected pixel-space means */
+  float*    depth;           /* [B,P]    */
+  float*    conic_opacity;   /* [B,P,4]  */
+  float*    rgb;             /* [B,P,3]  */
+  int32_t*  radii;           /* [B,P]    (also the `radii` return value) */
+  int32_t*  tiles_touched;   /* [B,P]    */
+  int32_t*  dup_offset;      /* [B,P]    exclusive prefix of tiles_touched (duplicate slots) */
+  int32_t*  control;         /* [spf_raster_control_ints(desc)] zeroed by forward; layout private,
+                                control[0] = total duplicates N, control[1] = overflow flag */
+  uint64_t* bucket;          /* [dup_capacity] (depth_bits<<32 | gaussian) grouped by tile */
+  float*    slab;            /* [dup_capacity,12] depth-sorted packed records per tile */
+  int32_t*  tile_ranges;     /* [B*T,2] start,end into slab */
+  float*    final_T;         /* [B,H,W] */
+  int32_t*  n_contrib;       /* [B,H,W] */
+} SpfRasterState;
+
+typedef struct {
+  float* color;              /* [B,3,H,W] */
+  float* depth;              /* [B,1,H,W] */
+  float* alpha;              /* [B,1,H,W] or NULL */
+} SpfRasterOut;
+
+typedef struct {
+  const float* dL_dcolor;    /* [B,3,H,W] or NULL */
+  const float* dL_ddepth;    /* [B,1,H,W] or NULL */
+  const float* dL_dalpha;    /* [B,1,H,W] or NULL */
+} SpfRasterGradOut;
+
+typedef struct {
+  float* dup_grad;           /* [dup_capacity,12] scratch: per-duplicate 2-D gradients */
+  float* pose_partial;       /* [B, NB, 16] scratch */
+  float* dL_dmeans3D;        /* [S,P,3] */
+  float* dL_dscales;         /* [S,P,3] */
+  float* dL_drotations;      /* [S,P,4] */
+  float* dL_dopacities;      /* [S,P]   */
+  float* dL_dshs;            /* same layout as shs, or NULL */
+  float* dL_dcolors;         /* [S,P,3] or NULL */
+  float* dL_dviewmatrix;     /* [B,16] */
+  float* dL_dmeans2D;        /* [B,P,3] or NULL: screen-space (NDC) mean gradients, the side channel
+                                of cuda_splatting.py:97-102 */
+} SpfRasterGradIn;
+
+SPF_API int         spf_version(void);
+SPF_API const char* spf_last_error(void);
+
+/* Number of int32 the `control` buffer needs. */
+SPF_API int64_t spf_raster_control_ints(const SpfRasterDesc* desc);
+
+/* Forward: projection + SH, tile binning, per-tile depth sort + slab pack, alpha blend.
+ * If the duplicate count exceeds desc->dup_capacity the overflow flag control[1] is set, the
+ * excess duplicates are dropped and the caller must re-run with a larger capacity
+ * (control[0] holds the exact count needed). */
+SPF_API int spf_raster_forward(const SpfRasterDesc* desc, const SpfRasterIn* in, SpfRasterState* st,
+                       SpfRasterOut* out, void* stream);
+
+/* Backward: blend backward (atomic-free, per-duplicate records) + projection/SH backward with
+ * camera-pose gradient. */
+SPF_API int spf_raster_backward(const SpfRasterDesc* desc, const SpfRasterIn* in, const SpfRasterState* st,
+                        const SpfRasterGradOut* gout, SpfRasterGradIn* gin, void* stream);
+
+/* Debug / parity helper: unpack gaussian ids (point_list) and (tile<<32|depth_bits) keys of the
+ * first n slab records into caller buffers (either may be NULL). */
+SPF_API int spf_raster_unpack_sorted(const SpfRasterDesc* desc, const SpfRasterState* st, int64_t n,
+                             int32_t* point_list, uint64_t* keys, void* stream);
+
+/* 2-D RoPE, in place.  Replaces rope_2d (curope.cpp:49-65).  tokens: [B,N,H,D] view with
+ * stride(3)==1, stride(2)==D (kernels.cu:91); positions int64 [B,N,2] contiguous.
+ * dtype: 0 = fp32, 1 = fp16, 2 = bf16.  fwd = +F0 forward, -F0 backward. */
+SPF_API int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
+               int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPFSPLAT_H_ */

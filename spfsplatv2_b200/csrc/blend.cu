@@ -1,0 +1,295 @@
+// K6 / K7: per-16x16-tile front-to-back alpha blend (forward) and its backward.
+//
+// One CTA (256 threads, one pixel each; warps own 8x4 pixel blocks) per (view, tile).  The tile's
+// depth-sorted slab -- contiguous 48-byte records {xy, conic, opacity, rgb, depth, slot, id} -- is
+// streamed through a double-buffered shared-memory ring with 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx); every thread then reads each record as three broadcast
+// LDS.128.
+//
+// Backward walks the list back to front (per pixel from its own n_contrib).  Per-Gaussian partial
+// gradients are reduced across the warp with shuffles (skipped when no lane of the warp touches
+// the Gaussian), across the 8 warps through shared memory in a fixed order, and written with ONE
+// plain store per (Gaussian, tile) duplicate into that duplicate's private slot: no atomics,
+// bit-reproducible.
+//
+// Replaces renderCUDA forward/backward of diff_gauss_pose (SURVEY.md App. B "Blend forward/backward").
+#include "spf_device.cuh"
+#include "spf_kernels.h"
+#include "spf_math.h"
+
+namespace spf {
+
+constexpr int CH_F = 128;  // records per forward chunk (6 KB)
+constexpr int CH_B = 64;   // records per backward chunk
+
+__device__ __forceinline__ void pixel_of_thread(int tid, int tile, int gx, int& px, int& py) {
+  const int w = tid >> 5, l = tid & 31;
+  const int tx = tile % gx, ty = tile / gx;
+  px = tx * TILE + (w & 1) * 8 + (l & 7);
+  py = ty * TILE + (w >> 1) * 4 + (l >> 3);
+}
+
+// alpha of one record at one pixel; shared by forward and backward so both make identical
+// accept / reject decisions.
+__device__ __forceinline__ bool eval_alpha(const float4& a, const float4& b, float pxf, float pyf, float& dx,
+                                           float& dy, float& G, float& alpha) {
+  dx = a.x - pxf;
+  dy = a.y - pyf;
+  const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+  if (power > 0.0f) return false;
+  G = expf(power);
+  alpha = fminf(ALPHA_MAX, b.y * G);
+  return alpha >= ALPHA_MIN;
+}
+
+template <bool TMA, int CH>
+__device__ __forceinline__ void stage_chunk(float4* dst, const float4* __restrict__ src, int cnt,
+                                            uint64_t* bar, int tid) {
+  if (TMA) {
+    if (tid == 0) {
+      mbar_expect_tx(bar, (uint32_t)cnt * 48u);
+      tma_load_1d(dst, src, (uint32_t)cnt * 48u, bar);
+    }
+  } else {
+    for (int i = tid; i < cnt * 3; i += TILE_THREADS) dst[i] = src[i];
+  }
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(TILE_THREADS)
+blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterOut out) {
+  __shared__ __align__(128) float4 buf[2][CH_F * 3];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x;
+  const int t = blockIdx.x;
+  const int view = t / d.T, tile = t - view * d.T;
+  const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
+  const int L = e - s;
+  int px, py;
+  pixel_of_thread(tid, tile, d.gx, px, py);
+  const bool inside = (px < d.W) && (py < d.H);
+  const float pxf = (float)px, pyf = (float)py;
+  if (TMA) {
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+  }
+  const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
+  const int nchunks = (L + CH_F - 1) / CH_F;
+
+  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+  int last = 0;
+  bool done = !inside;
+  int pending = -1;  // chunk whose TMA load is in flight beyond the current one
+
+  if (nchunks > 0) stage_chunk<TMA, CH_F>(buf[0], slab, min(CH_F, L), &bar[0], tid);
+  for (int c = 0; c < nchunks; ++c) {
+    const int cnt = min(CH_F, L - c * CH_F);
+    if (c + 1 < nchunks) {
+      stage_chunk<TMA, CH_F>(buf[(c + 1) & 1], slab + 3 * (size_t)(c + 1) * CH_F,
+                             min(CH_F, L - (c + 1) * CH_F), &bar[(c + 1) & 1], tid);
+      pending = c + 1;
+    } else {
+      pending = -1;
+    }
+    if (TMA) mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
+    else __syncthreads();
+    if (!done) {
+      const float4* rec = buf[c & 1];
+      const int base = c * CH_F;
+      for (int j = 0; j < cnt; ++j) {
+        const float4 a = rec[3 * j], b = rec[3 * j + 1];
+        float dx, dy, G, alpha;
+        if (!eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha)) continue;
+        const float test_T = T * (1.0f - alpha);
+        if (test_T < T_STOP) { done = true; break; }
+        const float4 cc = rec[3 * j + 2];
+        const float w = alpha * T;
+        C0 += b.z * w; C1 += b.w * w; C2 += cc.x * w; D += cc.y * w;
+        T = test_T;
+        last = base + j + 1;
+      }
+    }
+    if (__syncthreads_and(done)) break;
+  }
+  if (TMA && pending >= 0 && tid == 0) mbar_wait(&bar[pending & 1], (uint32_t)((pending >> 1) & 1));
+
+  if (inside) {
+    const float* bg = bg_all + view * 3;
+    const size_t hw = (size_t)d.H * d.W;
+    const size_t pix = (size_t)py * d.W + px;
+    float* col = out.color + (size_t)view * 3 * hw;
+    col[pix] = C0 + T * bg[0];
+    col[hw + pix] = C1 + T * bg[1];
+    col[2 * hw + pix] = C2 + T * bg[2];
+    out.depth[(size_t)view * hw + pix] = D;
+    if (out.alpha) out.alpha[(size_t)view * hw + pix] = 1.0f - T;
+    st.final_T[(size_t)view * hw + pix] = T;
+    st.n_contrib[(size_t)view * hw + pix] = last;
+  }
+}
+
+cudaError_t launch_blend_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                 const SpfRasterOut& out, cudaStream_t s) {
+  const int grid = d.B * d.T;
+  if (d.flags & SPF_FLAG_NO_TMA)
+    blend_forward_kernel<false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+  else
+    blend_forward_kernel<true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <bool TMA>
+__global__ void __launch_bounds__(TILE_THREADS)
+blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
+                      float* __restrict__ dup_grad) {
+  __shared__ __align__(128) float4 buf[2][CH_B * 3];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ float part[8][CH_B][10];
+  __shared__ unsigned long long hitmask[8];
+  __shared__ int max_contrib_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t = blockIdx.x;
+  const int view = t / d.T, tile = t - view * d.T;
+  const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
+  const int L = e - s;
+  if (L == 0) return;
+  int px, py;
+  pixel_of_thread(tid, tile, d.gx, px, py);
+  const bool inside = (px < d.W) && (py < d.H);
+  const float pxf = (float)px, pyf = (float)py;
+  const size_t hw = (size_t)d.H * d.W;
+  const size_t pix = (size_t)py * d.W + px;
+
+  if (tid == 0) {
+    max_contrib_s = 0;
+    if (TMA) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  }
+  __syncthreads();
+
+  float T_final = 1.0f, g0 = 0.f, g1 = 0.f, g2 = 0.f, gd = 0.f, ga = 0.f;
+  int ncontrib = 0;
+  if (inside) {
+    T_final = st.final_T[(size_t)view * hw + pix];
+    ncontrib = st.n_contrib[(size_t)view * hw + pix];
+    if (go.dL_dcolor) {
+      const float* gc = go.dL_dcolor + (size_t)view * 3 * hw;
+      g0 = gc[pix]; g1 = gc[hw + pix]; g2 = gc[2 * hw + pix];
+    }
+    if (go.dL_ddepth) gd = go.dL_ddepth[(size_t)view * hw + pix];
+    if (go.dL_dalpha) ga = go.dL_dalpha[(size_t)view * hw + pix];
+  }
+  {
+    int m = ncontrib;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) atomicMax(&max_contrib_s, m);
+  }
+  __syncthreads();
+  const int maxc = max_contrib_s;
+  const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
+
+  // duplicates nobody reached: zero gradient records
+  for (int i = maxc * 10 + tid; i < L * 10; i += TILE_THREADS) {
+    const int r = i / 10, k = i - r * 10;
+    const int slot = __float_as_int(__ldg(reinterpret_cast<const float*>(slab + 3 * r + 2) + 2));
+    dup_grad[(size_t)slot * 12 + k] = 0.0f;
+  }
+  if (maxc == 0) return;
+
+  const float* bg = bg_all + view * 3;
+  const float bgdot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2 - ga;
+  float T = T_final;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  float lv0 = 0.f, lv1 = 0.f, lv2 = 0.f, lv3 = 0.f, last_alpha = 0.f;
+
+  const int ctop = (maxc - 1) / CH_B;
+  {
+    const int cnt = min(CH_B, maxc - ctop * CH_B);
+    stage_chunk<TMA, CH_B>(buf[0], slab + 3 * (size_t)ctop * CH_B, cnt, &bar[0], tid);
+  }
+  int it = 0;
+  for (int c = ctop; c >= 0; --c, ++it) {
+    const int cnt = min(CH_B, maxc - c * CH_B);
+    if (c > 0)
+      stage_chunk<TMA, CH_B>(buf[(it + 1) & 1], slab + 3 * (size_t)(c - 1) * CH_B, CH_B, &bar[(it + 1) & 1], tid);
+    if (TMA) mbar_wait(&bar[it & 1], (uint32_t)((it >> 1) & 1));
+    else __syncthreads();
+
+    const float4* rec = buf[it & 1];
+    unsigned long long mymask = 0ull;
+    for (int j = cnt - 1; j >= 0; --j) {
+      const int idx = c * CH_B + j;
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] = 0.0f;
+      bool contrib = false;
+      if (idx < ncontrib) {
+        const float4 a = rec[3 * j], b = rec[3 * j + 1];
+        float dx, dy, G, alpha;
+        {
+          if (eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha)) {
+            contrib = true;
+            const float4 cc = rec[3 * j + 2];
+            T = T / (1.0f - alpha);
+            const float w = alpha * T;
+            float dL_dalpha = 0.0f;
+            acc0 = last_alpha * lv0 + (1.0f - last_alpha) * acc0; lv0 = b.z;  dL_dalpha += (b.z - acc0) * g0;
+            acc1 = last_alpha * lv1 + (1.0f - last_alpha) * acc1; lv1 = b.w;  dL_dalpha += (b.w - acc1) * g1;
+            acc2 = last_alpha * lv2 + (1.0f - last_alpha) * acc2; lv2 = cc.x; dL_dalpha += (cc.x - acc2) * g2;
+            acc3 = last_alpha * lv3 + (1.0f - last_alpha) * acc3; lv3 = cc.y; dL_dalpha += (cc.y - acc3) * gd;
+            dL_dalpha *= T;
+            last_alpha = alpha;
+            dL_dalpha += (-T_final / (1.0f - alpha)) * bgdot;
+            const float dL_dG = b.y * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddx = -gdx * a.z - gdy * a.w;
+            const float dG_ddy = -gdy * b.x - gdx * a.w;
+            v[0] = dL_dG * dG_ddx;
+            v[1] = dL_dG * dG_ddy;
+            v[2] = -0.5f * gdx * dx * dL_dG;
+            v[3] = -gdx * dy * dL_dG;
+            v[4] = -0.5f * gdy * dy * dL_dG;
+            v[5] = G * dL_dalpha;
+            v[6] = w * g0; v[7] = w * g1; v[8] = w * g2; v[9] = w * gd;
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, contrib)) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = warp_sum(v[k]);
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) part[wid][j][k] = v[k];
+        }
+        mymask |= (1ull << j);
+      }
+    }
+    if (lane == 0) hitmask[wid] = mymask;
+    __syncthreads();
+    // cross-warp reduction in fixed warp order, one plain store per (record, component)
+    for (int i = tid; i < cnt * 10; i += TILE_THREADS) {
+      const int j = i / 10, k = i - j * 10;
+      float sum = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if ((hitmask[w] >> j) & 1ull) sum += part[w][j][k];
+      const int slot = __float_as_int(reinterpret_cast<const float*>(rec + 3 * j + 2)[2]);
+      dup_grad[(size_t)slot * 12 + k] = sum;
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                  const SpfRasterGradOut& gout, const SpfRasterGradIn& gin, cudaStream_t s) {
+  const int grid = d.B * d.T;
+  if (d.flags & SPF_FLAG_NO_TMA)
+    blend_backward_kernel<false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+  else
+    blend_backward_kernel<true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+  return cudaGetLastError();
+}
+
+}  // namespace spf

@@ -1,0 +1,171 @@
+// extern "C" entry points of libspfsplat.so (see include/spfsplat.h).  Argument validation,
+// launch sequencing on the caller's stream, thread-local error text.  No allocation, no
+// synchronisation, no global mutable state.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "spf_kernels.h"
+#include "spf_math.h"
+
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(SPF_ERR_CUDA, "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+}
+
+bool make_dims(const SpfRasterDesc* desc, int sh_coeffs, bool use_sh, spf::Dims& d) {
+  d.S = desc->n_scenes;
+  d.v = desc->views_per_scene;
+  d.B = d.S * d.v;
+  d.P = desc->n_gaussians;
+  d.H = desc->image_height;
+  d.W = desc->image_width;
+  d.gx = (d.W + 15) / 16;
+  d.gy = (d.H + 15) / 16;
+  d.T = d.gx * d.gy;
+  d.NB = (d.P + spf::PROJ_THREADS - 1) / spf::PROJ_THREADS;
+  d.deg = desc->sh_degree;
+  d.K = (d.deg + 1) * (d.deg + 1);
+  d.flags = desc->flags;
+  d.mod = desc->scale_modifier;
+  d.cap = desc->dup_capacity;
+  (void)sh_coeffs; (void)use_sh;
+  return true;
+}
+
+int check_desc(const SpfRasterDesc* desc) {
+  if (!desc) return fail(SPF_ERR_BAD_ARG, "desc is NULL");
+  if (desc->n_scenes < 1 || desc->views_per_scene < 1 || desc->n_gaussians < 1)
+    return fail(SPF_ERR_BAD_ARG, "n_scenes, views_per_scene and n_gaussians must be >= 1");
+  if (desc->image_height < 1 || desc->image_width < 1) return fail(SPF_ERR_BAD_ARG, "bad image size");
+  if (desc->sh_degree < 0 || desc->sh_degree > 4) return fail(SPF_ERR_BAD_ARG, "sh_degree must be in 0..4");
+  if (desc->dup_capacity < 1 || desc->dup_capacity > 0x7fffffffLL)
+    return fail(SPF_ERR_BAD_ARG, "dup_capacity must be in 1..2^31-1");
+  if ((int64_t)desc->n_scenes * desc->views_per_scene > 65535)
+    return fail(SPF_ERR_UNSUPPORTED, "more than 65535 views per call");
+  if (desc->flags & SPF_FLAG_DEPTH_NORMALIZED) return fail(SPF_ERR_UNSUPPORTED, "normalised depth not implemented");
+  return 0;
+}
+
+int check_in(const SpfRasterDesc* desc, const SpfRasterIn* in) {
+  if (!in) return fail(SPF_ERR_BAD_ARG, "in is NULL");
+  if (!in->means3D || !in->scales || !in->rotations || !in->opacities)
+    return fail(SPF_ERR_BAD_ARG, "means3D / scales / rotations / opacities must be provided");
+  if ((in->shs != nullptr) == (in->colors_precomp != nullptr))
+    return fail(SPF_ERR_BAD_ARG, "Please provide exactly one of either SHs or precomputed colors!");
+  if (in->shs) {
+    const int K = (desc->sh_degree + 1) * (desc->sh_degree + 1);
+    if (in->sh_coeffs < K) return fail(SPF_ERR_BAD_ARG, "shs holds %d coefficients, degree %d needs %d",
+                                       in->sh_coeffs, desc->sh_degree, K);
+    if (in->sh_coeffs > spf::MAX_SH_COEFFS)
+      return fail(SPF_ERR_UNSUPPORTED, "at most %d SH coefficients per channel", spf::MAX_SH_COEFFS);
+  }
+  if (!in->viewmatrix || !in->projmatrix || !in->tanfov || !in->bg)
+    return fail(SPF_ERR_BAD_ARG, "viewmatrix / projmatrix / tanfov / bg must be provided");
+  if (reinterpret_cast<uintptr_t>(in->rotations) & 15) return fail(SPF_ERR_BAD_ARG, "rotations must be 16-byte aligned");
+  return 0;
+}
+
+int check_state(const SpfRasterState* st) {
+  if (!st) return fail(SPF_ERR_BAD_ARG, "state is NULL");
+  if (!st->xy || !st->depth || !st->conic_opacity || !st->rgb || !st->radii || !st->tiles_touched ||
+      !st->dup_offset || !st->control || !st->bucket || !st->slab || !st->tile_ranges || !st->final_T ||
+      !st->n_contrib)
+    return fail(SPF_ERR_BAD_ARG, "every SpfRasterState buffer must be provided");
+  if ((reinterpret_cast<uintptr_t>(st->slab) & 15) || (reinterpret_cast<uintptr_t>(st->conic_opacity) & 15) ||
+      (reinterpret_cast<uintptr_t>(st->xy) & 7) || (reinterpret_cast<uintptr_t>(st->bucket) & 7))
+    return fail(SPF_ERR_BAD_ARG, "state buffers are not sufficiently aligned (slab/conic 16 B, xy/bucket 8 B)");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int spf_version(void) { return 100; }
+
+const char* spf_last_error(void) { return g_err; }
+
+int64_t spf_raster_control_ints(const SpfRasterDesc* desc) {
+  if (check_desc(desc)) return -1;
+  spf::Dims d;
+  make_dims(desc, 0, false, d);
+  return spf::control_layout(d.B, d.T, d.NB).total;
+}
+
+int spf_raster_forward(const SpfRasterDesc* desc, const SpfRasterIn* in, SpfRasterState* st,
+                       SpfRasterOut* out, void* stream) {
+  int rc;
+  if ((rc = check_desc(desc)) || (rc = check_in(desc, in)) || (rc = check_state(st))) return rc;
+  if (!out || !out->color || !out->depth) return fail(SPF_ERR_BAD_ARG, "out.color / out.depth must be provided");
+  spf::Dims d;
+  make_dims(desc, in->sh_coeffs, in->shs != nullptr, d);
+  const spf::ControlLayout cl = spf::control_layout(d.B, d.T, d.NB);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(st->control, 0, (size_t)cl.total * sizeof(int32_t), s)) != cudaSuccess)
+    return cuda_fail(e, "memset(control)");
+  if ((e = spf::launch_project_forward(d, *in, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "project_forward");
+  if ((e = spf::launch_scan(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "scan");
+  if ((e = spf::launch_emit(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "emit");
+  if ((e = spf::launch_tile_sort_pack(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "tile_sort_pack");
+  if ((e = spf::launch_blend_forward(d, *in, *st, *out, s)) != cudaSuccess) return cuda_fail(e, "blend_forward");
+  g_err[0] = 0;
+  return SPF_OK;
+}
+
+int spf_raster_backward(const SpfRasterDesc* desc, const SpfRasterIn* in, const SpfRasterState* st,
+                        const SpfRasterGradOut* gout, SpfRasterGradIn* gin, void* stream) {
+  int rc;
+  if ((rc = check_desc(desc)) || (rc = check_in(desc, in)) || (rc = check_state(st))) return rc;
+  if (!gout || !gin) return fail(SPF_ERR_BAD_ARG, "gradient structs must be provided");
+  if (!gin->dup_grad || !gin->pose_partial || !gin->dL_dmeans3D || !gin->dL_dscales || !gin->dL_drotations ||
+      !gin->dL_dopacities || !gin->dL_dviewmatrix)
+    return fail(SPF_ERR_BAD_ARG, "dup_grad, pose_partial and the dL_d{means3D,scales,rotations,opacities,viewmatrix} buffers are required");
+  if (in->shs && !gin->dL_dshs) return fail(SPF_ERR_BAD_ARG, "dL_dshs is required when shs are given");
+  if ((reinterpret_cast<uintptr_t>(gin->dup_grad) & 15) || (reinterpret_cast<uintptr_t>(gin->dL_drotations) & 15))
+    return fail(SPF_ERR_BAD_ARG, "dup_grad / dL_drotations must be 16-byte aligned");
+  spf::Dims d;
+  make_dims(desc, in->sh_coeffs, in->shs != nullptr, d);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if ((e = spf::launch_blend_backward(d, *in, *st, *gout, *gin, s)) != cudaSuccess) return cuda_fail(e, "blend_backward");
+  if ((e = spf::launch_project_backward(d, *in, *st, *gin, s)) != cudaSuccess) return cuda_fail(e, "project_backward");
+  g_err[0] = 0;
+  return SPF_OK;
+}
+
+int spf_raster_unpack_sorted(const SpfRasterDesc* desc, const SpfRasterState* st, int64_t n,
+                             int32_t* point_list, uint64_t* keys, void* stream) {
+  int rc;
+  if ((rc = check_desc(desc)) || (rc = check_state(st))) return rc;
+  if (n < 0 || n > desc->dup_capacity) return fail(SPF_ERR_BAD_ARG, "n out of range");
+  spf::Dims d;
+  make_dims(desc, 0, false, d);
+  const spf::ControlLayout cl = spf::control_layout(d.B, d.T, d.NB);
+  cudaError_t e = spf::launch_unpack_sorted(d, *st, n, point_list, keys, cl, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "unpack_sorted");
+  return SPF_OK;
+}
+
+int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
+               int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
+  if (!tokens || !positions) return fail(SPF_ERR_BAD_ARG, "tokens / positions are NULL");
+  if (B < 0 || N < 0 || H < 0 || D < 0) return fail(SPF_ERR_BAD_ARG, "negative size");
+  if (D % 4 != 0) return fail(SPF_ERR_BAD_ARG, "token dim must be multiple of 4");
+  if (dtype < 0 || dtype > 2) return fail(SPF_ERR_BAD_ARG, "dtype must be 0 (fp32), 1 (fp16) or 2 (bf16)");
+  cudaError_t e = spf::launch_rope2d(tokens, positions, B, N, H, D, stride_b, stride_n, dtype, base, fwd,
+                                     static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "rope2d");
+  return SPF_OK;
+}
+
+}  // extern "C"

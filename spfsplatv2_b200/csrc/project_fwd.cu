@@ -1,0 +1,122 @@
+// K1: per-Gaussian 3-D -> 2-D EWA projection, 2-D covariance / conic / radius / tile rectangle and
+// SH -> RGB, for all B views of a batched call.  One thread per (view, Gaussian); a block's 128 SH
+// records (128 x 300 B at degree 4) are staged through shared memory with 128-bit coalesced loads
+// and read back conflict-free (odd stride).
+//
+// THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: radii, rectangles and depth keys must be
+// bit-identical to oracle/raster_oracle.py (see spf_math.h).
+//
+// Replaces the preprocess stage of diff_gauss_pose (call site
+// /root/reference/src/model/decoder/cuda_splatting.py:128-138; algorithm SURVEY.md App. B 1-10).
+#include "spf_device.cuh"
+#include "spf_kernels.h"
+#include "spf_math.h"
+
+namespace spf {
+
+__global__ void __launch_bounds__(PROJ_THREADS)
+project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
+                       int* __restrict__ block_sum) {
+  extern __shared__ __align__(16) float sh_s[];
+  __shared__ ViewConsts vc;
+  __shared__ int warp_tot[PROJ_THREADS / 32];
+
+  const int tid = threadIdx.x;
+  const int view = blockIdx.y;
+  const int scene = view / d.v;
+  const int g0 = blockIdx.x * PROJ_THREADS;
+  const int g = g0 + tid;
+  const int nvalid = min(PROJ_THREADS, d.P - g0);
+  const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
+
+  if (tid == 0) {
+    float V[16], Pm[16], bg[3];
+    for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[view * 16 + i]; Pm[i] = in.projmatrix[view * 16 + i]; }
+    for (int i = 0; i < 3; ++i) bg[i] = in.bg[view * 3 + i];
+    make_view_consts(vc, V, Pm, in.tanfov[view * 2], in.tanfov[view * 2 + 1], bg, d.mod, d.W, d.H);
+  }
+  const int row = 3 * in.sh_coeffs;
+  const int stride = (row & 1) ? row : row + 1;
+  if (in.shs) {
+    const float* src = in.shs + ((size_t)scene * d.P + g0) * row;
+    block_copy_g2s(sh_s, src, nvalid * row, row, stride, tid, PROJ_THREADS);
+  }
+  __syncthreads();
+
+  int tiles = 0;
+  if (g < d.P) {
+    const size_t sg = (size_t)scene * d.P + g;
+    const size_t vg = (size_t)view * d.P + g;
+    float m[3], s[3], q[4];
+    for (int i = 0; i < 3; ++i) {
+      m[i] = __ldg(in.means3D + sg * 3 + i) * ps;
+      s[i] = __ldg(in.scales + sg * 3 + i) * ps;
+    }
+    {
+      const float4 qq = __ldg(reinterpret_cast<const float4*>(in.rotations) + sg);
+      if (d.flags & SPF_FLAG_QUAT_XYZW) { q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z; }
+      else { q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w; }
+    }
+    Projected o;
+    const bool vis = project_forward(vc, m, s, q, o);
+    tiles = o.tiles;
+
+    float rgb[3];
+    if (in.shs) {
+      const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
+      const float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
+      float Bk[MAX_SH_COEFFS];
+      sh_basis(d.deg, dx * inv, dy * inv, dz * inv, Bk);
+      const float* mysh = sh_s + tid * stride;
+      const bool ck = (d.flags & SPF_FLAG_SH_LAYOUT_CK) != 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float acc = 0.0f;
+        for (int k = 0; k < d.K; ++k) acc += Bk[k] * (ck ? mysh[c * in.sh_coeffs + k] : mysh[k * 3 + c]);
+        rgb[c] = fmaxf(acc + 0.5f, 0.0f);
+      }
+    } else {
+      for (int c = 0; c < 3; ++c) rgb[c] = __ldg(in.colors_precomp + sg * 3 + c);
+    }
+
+    reinterpret_cast<float2*>(st.xy)[vg] = make_float2(o.px, o.py);
+    st.depth[vg] = o.depth;
+    reinterpret_cast<float4*>(st.conic_opacity)[vg] =
+        make_float4(o.conx, o.cony, o.conz, __ldg(in.opacities + sg));
+    st.rgb[vg * 3 + 0] = rgb[0]; st.rgb[vg * 3 + 1] = rgb[1]; st.rgb[vg * 3 + 2] = rgb[2];
+    st.radii[vg] = o.radius;
+    st.tiles_touched[vg] = o.tiles;
+    if (vis) {
+      int* tc = tile_count + (size_t)view * d.T;
+      for (int y = o.ry0; y < o.ry1; ++y)
+        for (int x = o.rx0; x < o.rx1; ++x) atomicAdd(tc + y * d.gx + x, 1);
+    }
+  }
+  // block total of tiles_touched (for the duplicate-slot prefix sums)
+  const int wsum = warp_sum_i(tiles);
+  if ((tid & 31) == 0) warp_tot[tid >> 5] = wsum;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < PROJ_THREADS / 32; ++w) t += warp_tot[w];
+    block_sum[(size_t)view * d.NB + blockIdx.x] = t;
+  }
+}
+
+cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                   const ControlLayout& cl, cudaStream_t s) {
+  const int row = 3 * in.sh_coeffs;
+  const int stride = (row & 1) ? row : row + 1;
+  const size_t smem = in.shs ? (size_t)PROJ_THREADS * stride * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(project_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid(d.NB, d.B);
+  project_forward_kernel<<<grid, PROJ_THREADS, smem, s>>>(d, in, st, st.control + cl.tile_count,
+                                                          st.control + cl.block_sum);
+  return cudaGetLastError();
+}
+
+}  // namespace spf

@@ -1,0 +1,56 @@
+// Internal launcher declarations shared by capi.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spfsplat.h"
+
+namespace spf {
+
+constexpr int PROJ_THREADS = 128;   // Gaussians per projection block
+constexpr int TILE_THREADS = 256;   // 16x16 pixels
+constexpr int SORT_SMEM_CAP = 4096; // per-tile list length sorted in shared memory
+
+// control buffer layout (int32 words)
+struct ControlLayout {
+  int64_t n_total, overflow, tile_count, tile_cursor, tile_start, block_sum, block_off, total;
+};
+inline ControlLayout control_layout(int B, int T, int NB) {
+  ControlLayout c;
+  c.n_total = 0;
+  c.overflow = 1;
+  int64_t o = 4;
+  c.tile_count = o;  o += (int64_t)B * T;
+  c.tile_cursor = o; o += (int64_t)B * T;
+  c.tile_start = o;  o += (int64_t)B * T + 1;
+  c.block_sum = o;   o += (int64_t)B * NB;
+  c.block_off = o;   o += (int64_t)B * NB + 1;
+  c.total = (o + 3) & ~int64_t(3);
+  return c;
+}
+
+struct Dims {
+  int S, v, B, P, H, W, gx, gy, T, NB, K, deg;
+  uint32_t flags;
+  float mod;
+  int64_t cap;
+};
+
+cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                   const ControlLayout& cl, cudaStream_t s);
+cudaError_t launch_scan(const Dims& d, const SpfRasterState& st, const ControlLayout& cl, cudaStream_t s);
+cudaError_t launch_emit(const Dims& d, const SpfRasterState& st, const ControlLayout& cl, cudaStream_t s);
+cudaError_t launch_tile_sort_pack(const Dims& d, const SpfRasterState& st, const ControlLayout& cl,
+                                  cudaStream_t s);
+cudaError_t launch_blend_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                 const SpfRasterOut& out, cudaStream_t s);
+cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                  const SpfRasterGradOut& gout, const SpfRasterGradIn& gin, cudaStream_t s);
+cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                    const SpfRasterGradIn& gin, cudaStream_t s);
+cudaError_t launch_unpack_sorted(const Dims& d, const SpfRasterState& st, int64_t n, int32_t* point_list,
+                                 uint64_t* keys, const ControlLayout& cl, cudaStream_t s);
+cudaError_t launch_rope2d(void* tokens, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
+                          int64_t sn, int dtype, float base, float fwd, cudaStream_t s);
+
+}  // namespace spf

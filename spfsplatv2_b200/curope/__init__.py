@@ -1,0 +1,79 @@
+"""Drop-in module for the reference's ``curope`` extension
+(/root/reference/src/model/encoder/backbone/croco/curope/curope.cpp:49-69): ``rope_2d(tokens,
+positions, base, fwd)`` rotates ``tokens`` [B,N,H,D] IN PLACE.  Also ``cuRoPE2D`` / ``cuRoPE2D_func``
+with the interface of curope2d.py:12-40."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def rope_2d(tokens: torch.Tensor, positions: torch.Tensor, base: float, fwd: float) -> None:
+    # same argument checks (and messages) as curope.cpp:54-59 / kernels.cu:91-94
+    if tokens.dim() != 4:
+        raise RuntimeError("tokens must have 4 dimensions")
+    if positions.dim() != 3:
+        raise RuntimeError("positions must have 3 dimensions")
+    if tokens.size(0) != positions.size(0):
+        raise RuntimeError("batch size differs between tokens & positions")
+    if tokens.size(1) != positions.size(1):
+        raise RuntimeError("seq_length differs between tokens & positions")
+    if positions.size(2) != 2:
+        raise RuntimeError("positions.shape[2] must be equal to 2")
+    if tokens.is_cuda != positions.is_cuda:
+        raise RuntimeError("tokens and positions are not on the same device")
+    if not tokens.is_cuda:
+        raise RuntimeError("spfsplatv2_b200.curope: CUDA tensors required (no CPU fallback on the product path)")
+    B, N, H, D = tokens.shape
+    if not (tokens.stride(3) == 1 and tokens.stride(2) == D):
+        raise RuntimeError("tokens are not contiguous")
+    if not positions.is_contiguous():
+        raise RuntimeError("positions are not contiguous")
+    if D % 4 != 0:
+        raise RuntimeError("token dim must be multiple of 4")
+    if tokens.dtype not in _DTYPES:
+        raise RuntimeError(f"unsupported dtype {tokens.dtype}")
+    if positions.dtype != torch.int64:
+        raise RuntimeError("positions must be int64")
+    stream = C.c_void_p(torch.cuda.current_stream(tokens.device).cuda_stream)
+    with torch.cuda.device(tokens.device):
+        rc = L.lib().spf_rope2d(C.c_void_p(tokens.data_ptr()), C.c_void_p(positions.data_ptr()), B, N, H, D,
+                                tokens.stride(0), tokens.stride(1), _DTYPES[tokens.dtype], float(base), float(fwd),
+                                stream)
+    L.check(rc, "spf_rope2d")
+
+
+class cuRoPE2D_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tokens, positions, base, F0=1):
+        ctx.save_for_backward(positions)
+        ctx.saved_base = base
+        ctx.saved_F0 = F0
+        rope_2d(tokens, positions, base, F0)
+        ctx.mark_dirty(tokens)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, grad_res):
+        (positions,) = ctx.saved_tensors
+        if not (grad_res.stride(3) == 1 and grad_res.stride(2) == grad_res.size(3)):
+            grad_res = grad_res.contiguous()
+        rope_2d(grad_res, positions, ctx.saved_base, -ctx.saved_F0)
+        ctx.mark_dirty(grad_res)
+        return grad_res, None, None, None
+
+
+class cuRoPE2D(torch.nn.Module):
+    def __init__(self, freq=100.0, F0=1.0):
+        super().__init__()
+        self.base = freq
+        self.F0 = F0
+
+    def forward(self, tokens, positions):
+        cuRoPE2D_func.apply(tokens.transpose(1, 2), positions, self.base, self.F0)
+        return tokens

@@ -1,0 +1,232 @@
+"""Batched differentiable Gaussian rasterizer: torch.autograd.Function over the C-ABI library.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); all arithmetic runs in
+libspfsplat.so.  One call renders B = S*v views (view i reads scene i // v) with one launch
+sequence, replacing the reference's per-view Python loop around diff_gauss_pose
+(/root/reference/src/model/decoder/cuda_splatting.py:96-143).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+TILE = 16
+PROJ_THREADS = 128
+
+# Duplicate-buffer capacity policy: no device->host wait before the kernels are enqueued.  The buffers
+# are sized from a per-shape high-water mark; the exact count N comes back through pinned memory while
+# the blend kernel is already running, and the forward is re-run (rare) if N exceeded the capacity.
+_capacity_hint: dict = {}
+GROWTH = 1.25
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+@dataclass
+class RasterSettings:
+    image_height: int
+    image_width: int
+    sh_degree: int
+    scale_modifier: float = 1.0
+    views_per_scene: int = 1
+    sh_layout_ck: bool = False          # shs given as [S,P,3,K] (encoder-native) instead of [S,P,K,3]
+    enable_cov_grad: bool = True
+    enable_sh_grad: bool = True
+    quat_xyzw: bool = False
+    want_alpha: bool = False
+    want_means2d_grad: bool = False
+    no_tma: bool = False
+
+    def flags(self) -> int:
+        f = 0
+        if self.sh_layout_ck:
+            f |= L.SPF_FLAG_SH_LAYOUT_CK
+        if not self.enable_cov_grad:
+            f |= L.SPF_FLAG_NO_COV_GRAD
+        if not self.enable_sh_grad:
+            f |= L.SPF_FLAG_NO_SH_GRAD
+        if self.quat_xyzw:
+            f |= L.SPF_FLAG_QUAT_XYZW
+        if self.no_tma or os.environ.get("SPF_NO_TMA") == "1":
+            f |= L.SPF_FLAG_NO_TMA
+        return f
+
+
+class _State:
+    """Forward intermediates kept for backward / inspection (plain tensors, not autograd-tracked)."""
+    __slots__ = ("desc", "cin", "cstate", "keep", "n_dups", "capacity", "tensors")
+
+
+def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg,
+                  pre_scale):
+    lib = L.lib()
+    dev = means.device
+    if dev.type != "cuda":
+        raise RuntimeError("spfsplatv2_b200 rasterizer needs CUDA tensors (no CPU fallback)")
+    S, P = means.shape[0], means.shape[1]
+    v = s.views_per_scene
+    B = S * v
+    H, W = s.image_height, s.image_width
+    if viewmat.shape[0] != B:
+        raise ValueError(f"viewmatrix has {viewmat.shape[0]} views, expected n_scenes*views_per_scene={B}")
+    T = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
+    use_sh = shs is not None
+    if use_sh == (colors is not None):
+        raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+    K = 0
+    if use_sh:
+        K = shs.shape[-1] if s.sh_layout_ck else shs.shape[-2]
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    key = (dev.index, S, v, P, H, W)
+    cap = max(int(_capacity_hint.get(key, 2 * B * P)), 1024)
+
+    desc = L.SpfRasterDesc(S, v, P, H, W, s.sh_degree, s.flags(), float(s.scale_modifier), cap)
+    n_ctrl = lib.spf_raster_control_ints(C.byref(desc))
+    if n_ctrl < 0:
+        L.check(-1, "spf_raster_control_ints")
+
+    cin = L.SpfRasterIn(_ptr(means), _ptr(scales), _ptr(rots), _ptr(opac), _ptr(shs), _ptr(colors), K,
+                        _ptr(viewmat), _ptr(projmat), _ptr(tanfov), _ptr(bg), _ptr(pre_scale))
+    t = dict(
+        xy=torch.empty(B, P, 2, **f32), depth=torch.empty(B, P, **f32), conic_opacity=torch.empty(B, P, 4, **f32),
+        rgb=torch.empty(B, P, 3, **f32), radii=torch.empty(B, P, **i32), tiles_touched=torch.empty(B, P, **i32),
+        dup_offset=torch.empty(B, P, **i32), control=torch.empty(n_ctrl, **i32),
+        tile_ranges=torch.empty(B * T, 2, **i32), final_T=torch.empty(B, H, W, **f32),
+        n_contrib=torch.empty(B, H, W, **i32))
+    color = torch.empty(B, 3, H, W, **f32)
+    depth = torch.empty(B, 1, H, W, **f32)
+    alpha = torch.empty(B, 1, H, W, **f32) if s.want_alpha else None
+    host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+    stream = _stream(dev)
+    while True:
+        desc.dup_capacity = cap
+        t["bucket"] = torch.empty(cap, dtype=torch.int64, device=dev)
+        t["slab"] = torch.empty(cap, 12, **f32)
+        cstate = L.SpfRasterState(*[_ptr(t[k]) for k in ("xy", "depth", "conic_opacity", "rgb", "radii",
+                                                        "tiles_touched", "dup_offset", "control", "bucket",
+                                                        "slab", "tile_ranges", "final_T", "n_contrib")])
+        cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
+        L.check(lib.spf_raster_forward(C.byref(desc), C.byref(cin), C.byref(cstate), C.byref(cout), stream),
+                "spf_raster_forward")
+        host.copy_(t["control"][:2], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        ev.synchronize()   # waits for the tiny copy only in stream order; all kernels are already enqueued
+        n_dups, overflow = int(host[0]), int(host[1])
+        if n_dups <= cap and not overflow:
+            break
+        cap = int(n_dups * 1.05) + 1024
+    _capacity_hint[key] = max(int(n_dups * GROWTH) + 1024, 1024)
+
+    st = _State()
+    st.desc, st.cin, st.cstate, st.n_dups, st.capacity, st.tensors = desc, cin, cstate, n_dups, cap, t
+    st.keep = (means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale)
+    return color, depth, alpha, t["radii"], st
+
+
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, settings: RasterSettings, means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov,
+                bg, pre_scale, means2d):
+        args = [None if a is None else _f32c(a.detach()) for a in
+                (means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale)]
+        color, depth, alpha, radii, st = _forward_impl(settings, *args)
+        ctx.settings = settings
+        ctx.st = st
+        ctx.shapes = (means.shape, scales.shape, rots.shape, opac.shape,
+                      None if shs is None else shs.shape, None if colors is None else colors.shape,
+                      viewmat.shape, None if means2d is None else means2d.shape)
+        ctx.mark_non_differentiable(radii)
+        if alpha is None:
+            alpha = torch.empty(0, device=color.device)
+            ctx.mark_non_differentiable(alpha)
+        return color, depth, alpha, radii
+
+    @staticmethod
+    def backward(ctx, g_color, g_depth, g_alpha, _g_radii):
+        s: RasterSettings = ctx.settings
+        st: _State = ctx.st
+        lib = L.lib()
+        means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale = st.keep
+        dev = means.device
+        S, P = means.shape[0], means.shape[1]
+        B = S * s.views_per_scene
+        NB = (P + PROJ_THREADS - 1) // PROJ_THREADS
+        f32 = dict(dtype=torch.float32, device=dev)
+        gc = None if g_color is None else _f32c(g_color)
+        gd = None if g_depth is None else _f32c(g_depth)
+        ga = None if (g_alpha is None or not s.want_alpha) else _f32c(g_alpha)
+        gout = L.SpfRasterGradOut(_ptr(gc), _ptr(gd), _ptr(ga))
+        dup_grad = torch.empty(max(st.n_dups, 1), 12, **f32)
+        pose_partial = torch.empty(B, NB, 16, **f32)
+        d_means = torch.empty_like(means)
+        d_scales = torch.empty_like(scales)
+        d_rots = torch.empty_like(rots)
+        d_opac = torch.empty_like(opac)
+        d_shs = torch.empty_like(shs) if shs is not None else None
+        d_cols = torch.empty_like(colors) if colors is not None else None
+        d_view = torch.empty(B, 16, **f32)
+        d_m2d = torch.empty(B, P, 3, **f32) if (s.want_means2d_grad and ctx.shapes[7] is not None) else None
+        gin = L.SpfRasterGradIn(_ptr(dup_grad), _ptr(pose_partial), _ptr(d_means), _ptr(d_scales), _ptr(d_rots),
+                                _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
+        L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
+                                        C.byref(gin), _stream(dev)), "spf_raster_backward")
+        sh = ctx.shapes
+        return (None, d_means.view(sh[0]), d_scales.view(sh[1]), d_rots.view(sh[2]), d_opac.view(sh[3]),
+                None if d_shs is None else d_shs.view(sh[4]), None if d_cols is None else d_cols.view(sh[5]),
+                d_view.view(sh[6]), None, None, None, None,
+                None if d_m2d is None else d_m2d.view(sh[7]))
+
+
+def rasterize_batched(settings: RasterSettings, means: Tensor, scales: Tensor, rotations: Tensor,
+                      opacities: Tensor, shs: Optional[Tensor], colors: Optional[Tensor], viewmatrix: Tensor,
+                      projmatrix: Tensor, tanfov: Tensor, bg: Tensor, pre_scale: Optional[Tensor] = None,
+                      means2d: Optional[Tensor] = None):
+    """means [S,P,3], scales [S,P,3], rotations [S,P,4], opacities [S,P], shs [S,P,K,3] (or [S,P,3,K] with
+    settings.sh_layout_ck) or colors [S,P,3]; viewmatrix/projmatrix [B,4,4] (row-vector convention),
+    tanfov [B,2], bg [B,3], pre_scale [B] or None.  Returns (color [B,3,H,W], depth [B,1,H,W],
+    alpha [B,1,H,W] or empty, radii [B,P] int32).  Differentiable wrt means, scales, rotations,
+    opacities, shs/colors and viewmatrix."""
+    return _Rasterize.apply(settings, means, scales, rotations, opacities, shs, colors, viewmatrix, projmatrix,
+                            tanfov, bg, pre_scale, means2d)
+
+
+def forward_with_state(settings: RasterSettings, means, scales, rotations, opacities, shs, colors, viewmatrix,
+                       projmatrix, tanfov, bg, pre_scale=None):
+    """No-autograd forward that also returns the intermediate state (for parity tests / profiling)."""
+    args = [None if a is None else _f32c(a.detach()) for a in
+            (means, scales, rotations, opacities, shs, colors, viewmatrix, projmatrix, tanfov, bg, pre_scale)]
+    return _forward_impl(settings, *args)
+
+
+def unpack_sorted(st: _State):
+    """(point_list int32 [N], keys int64 [N]) of the sorted duplicate list -- parity helper."""
+    n = st.n_dups
+    dev = st.tensors["slab"].device
+    pl = torch.empty(n, dtype=torch.int32, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    L.check(L.lib().spf_raster_unpack_sorted(C.byref(st.desc), C.byref(st.cstate), n, _ptr(pl), _ptr(keys),
+                                             _stream(dev)), "spf_raster_unpack_sorted")
+    return pl, keys
