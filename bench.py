@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- views/sec, forward+backward, of the splatting decoder hot path on synthetic SPFSplatV2-shaped
+scenes (BASELINE.json metric).  One process per GPU; see the module-level contract in the task statement.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the CPU oracle port on the host cores (reference rasterizer
+                                             # diff_gauss_pose is not vendored / installable: SURVEY.md §0)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "views/sec fwd+bwd @256x256, 65k Gaussians"
+UNIT = "views/s"
+
+WORKLOADS = {
+    # name: (v_cxt, h, w, scenes_per_step, description)
+    "c2p": (1, 256, 256, 16, "headline: 256x256, P=65536 Gaussians/scene (1 context view), SH deg 4, 16 scenes x 1 target view per step"),
+    "c2": (2, 256, 256, 16, "re10k 2-view 256x256, P=131072, 16 scenes x 1 target view per step"),
+    "c3": (10, 256, 256, 3, "re10k 10-view 256x256, P=655360, 3 scenes x 1 target view per step"),
+    "c4": (2, 512, 512, 4, "acid 2-view 512x512, P=524288, 4 scenes x 1 target view per step"),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _make_inputs(workload: str, rank: int, pin: bool):
+    from spfsplatv2_b200.synthetic import make_batch
+    v_cxt, h, w, b, _ = WORKLOADS[workload]
+    sc = make_batch(b, seed=1000 * rank, v_cxt=v_cxt, h=h, w=w, regime="init", n_target=1)
+    gt = make_batch(b, seed=1000 * rank + 500, v_cxt=1, h=h, w=w, regime="init", n_target=1)  # only for a pseudo-GT pose
+    host = dict(means=sc.means, rotations=sc.rotations, scales=sc.scales, harmonics=sc.harmonics,
+                opacities=sc.opacities, extrinsics=sc.extrinsics, intrinsics=sc.intrinsics, near=sc.near, far=sc.far)
+    host["gt"] = torch.rand(b, 1, 3, h, w, generator=torch.Generator().manual_seed(rank))
+    if pin:
+        host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    return sc, host
+
+
+def _step(dec, G, dev_in, leaves_keys=("means", "rotations", "scales", "harmonics", "opacities")):
+    """One fwd+bwd of the decoder through the public API; returns the loss tensor."""
+    leaves = {k: dev_in[k].detach().requires_grad_() for k in leaves_keys}
+    ext = dev_in["extrinsics"].detach().requires_grad_()
+    g = G(leaves["means"], dev_in["cov"], leaves["rotations"], leaves["scales"], leaves["harmonics"], leaves["opacities"])
+    out = dec(g, ext, dev_in["intrinsics"], dev_in["near"], dev_in["far"], dev_in["shape"])
+    loss = ((out.color - dev_in["gt"]) ** 2).mean()
+    loss.backward()
+    return loss, leaves, ext
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from spfsplatv2_b200.camera import camera_setup
+    from spfsplatv2_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg, Gaussians
+    from spfsplatv2_b200.rasterizer import RasterSettings, profile_stages
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    v_cxt, h, w, b, desc = WORKLOADS[args.workload]
+    sc, host = _make_inputs(args.workload, rank, pin=True)
+    P = sc.means.shape[1]
+    dec = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], True, True, True)).to(dev)
+    dev_in = {k: v.to(dev) for k, v in host.items()}
+    dev_in["cov"] = torch.zeros(1, 1, 3, 3, device=dev).expand(b, P, 3, 3)   # never read by the decoder
+    dev_in["shape"] = (h, w)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    # stand-in for the replicated-parameter gradient all-reduce of the DDP training step
+    ar_buf = torch.zeros(16 * 1024 * 1024, device=dev) if world > 1 else None
+    ar_stream = torch.cuda.Stream(dev) if world > 1 else None
+
+    def step_resident():
+        loss, leaves, ext = _step(dec, Gaussians, dev_in)
+        if world > 1:
+            ar_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(ar_stream):
+                dist.all_reduce(ar_buf)
+        return loss
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        d["cov"], d["shape"] = dev_in["cov"], (h, w)
+        loss, leaves, ext = _step(dec, Gaussians, d)
+        if world > 1:
+            ar_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(ar_stream):
+                dist.all_reduce(ar_buf)
+        return float(loss.item())      # device->host read of the step's result
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(ar_stream)
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(ar_stream)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([ms, wall], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, wall = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+
+    views_total = b * world
+    value = views_total * args.steps / (ms / 1e3)
+    e2e_value = views_total * args.steps / (max(ms_e2e, wall_e2e) / 1e3)
+
+    line = None
+    if rank == 0:
+        peaks, peak_kind = _peaks()
+        # per-kernel device times with CUDA events around every stage of the launch sequence
+        view, proj, tanfov, scale = camera_setup(dev_in["extrinsics"].reshape(b, 4, 4), dev_in["intrinsics"].reshape(b, 3, 3),
+                                                 dev_in["near"].reshape(-1), dev_in["far"].reshape(-1), True)
+        rs = RasterSettings(h, w, 4, 1.0, 1, sh_layout_ck=True)
+        gcol = torch.randn(b, 3, h, w, device=dev) / (b * 3 * h * w)
+        st = profile_stages(rs, dev_in["means"], dev_in["scales"], dev_in["rotations"], dev_in["opacities"],
+                            dev_in["harmonics"], None, view, proj, tanfov, torch.zeros(b, 3, device=dev), scale,
+                            gcol, None, iters=max(5, args.steps))
+        N = st.pop("_n_dups")
+        HW = h * w
+        algo = {   # SURVEY.md §8(d) per-unit figures x units per launch (B views); see DESIGN.md
+            "project_forward": 392.0 * P * b,
+            "blend_forward": 44.0 * N + 24.0 * HW * b,
+            "blend_backward": 44.0 * N + 36.0 * HW * b + 40.0 * P * b,
+            "project_backward": 776.0 * P * b,
+            "tile_sort_pack": 140.0 * N,
+        }
+        top = max((k for k in st if k in algo), key=lambda k: st[k])
+        achieved = algo[top] / (st[top] * 1e-3) / 1e9
+        step_bytes = 1208.0 * P * b + 228.0 * N + 60.0 * HW * b
+        kern_ms = sum(st.values())
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "views_per_step_per_gpu": b, "gaussians_per_scene": P,
+                       "duplicates_per_step": N, "image": [h, w], "sh_degree": 4,
+                       "parallelism": f"dp{world} (scenes sharded over ranks; 64 MiB stand-in grad all-reduce/step)" if world > 1 else "single GPU",
+                       "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step > 126 MB L2, no explicit flush"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(max(ms_e2e, wall_e2e) / args.steps, 4)},
+            "gpu_launches": 8 * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
+                         "traffic": None, "kernel_ms": round(st[top], 4),
+                         "kernel_share_of_step": round(st[top] / kern_ms, 3)},
+            "stage_ms": {k: round(v, 4) for k, v in st.items()},
+            "stage_gbs": {k: round(algo[k] / (st[k] * 1e-3) / 1e9, 1) for k in algo},
+            "step_roofline": {"bytes_per_view": round(step_bytes / b), "achieved_gbs": round(step_bytes * world / (ms / args.steps * 1e-3) / 1e9, 1),
+                              "frac": round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+            "wall_ms_per_step": round(wall / args.steps, 4),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload, sample_views=args.cpu_views)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload: str, sample_views: int = 3) -> dict:
+    """The oracle (pure-PyTorch CPU alpha-blend port of the path) timed fwd+bwd on the host cores, on a
+    bounded sample of the same workload."""
+    from spfsplatv2_b200.synthetic import make_scene
+    from tests.util import oracle_views
+    v_cxt, h, w, b, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t_tot = 0.0
+    for i in range(sample_views):
+        sc = make_scene(seed=i, v_cxt=v_cxt, h=h, w=w, regime="init", n_target=1)
+        gt = torch.rand(3, h, w, generator=torch.Generator().manual_seed(i))
+        t0 = time.perf_counter()
+        res, leaves = oracle_views(sc, requires_grad=True)
+        ((res[0]["color"] - gt) ** 2).mean().backward()
+        t_tot += time.perf_counter() - t0
+    return {"value": round(sample_views / t_tot, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_views} views of workload {workload} (fwd+bwd, torch CPU, {cores} threads)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v_cxt, h, w, b, desc = WORKLOADS[args.workload]
+    from spfsplatv2_b200.synthetic import make_scene
+    from tests.util import oracle_views
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps, warmup = args.steps, args.warmup
+    # each step = a bounded sample (1 view) of the workload; cap the run to a few minutes
+    steps = min(steps, 20)
+    warmup = min(warmup, 1)
+    times = []
+    for i in range(warmup + steps):
+        sc = make_scene(seed=i, v_cxt=v_cxt, h=h, w=w, regime="init", n_target=1)
+        gt = torch.rand(3, h, w, generator=torch.Generator().manual_seed(i))
+        t0 = time.perf_counter()
+        res, leaves = oracle_views(sc, requires_grad=True)
+        ((res[0]["color"] - gt) ** 2).mean().backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if sum(times) > 150:
+            break
+    n = len(times)
+    value = n / sum(times)
+    P = v_cxt * h * w
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": n, "warmup": warmup,
+            "ms_per_step": round(1e3 * sum(times) / n, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "gaussians_per_scene": P, "image": [h, w], "sh_degree": 4,
+                       "note": "reference CUDA rasterizer diff_gauss_pose is not vendored/installable; this is the CPU oracle port"},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"1 view per step, {n} steps, torch CPU {cores} threads"},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-views", type=int, default=4)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

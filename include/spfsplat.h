@@ -147,6 +147,17 @@ SPF_API int spf_raster_forward(const SpfRasterDesc* desc, const SpfRasterIn* in,
 SPF_API int spf_raster_backward(const SpfRasterDesc* desc, const SpfRasterIn* in, const SpfRasterState* st,
                         const SpfRasterGradOut* gout, SpfRasterGradIn* gin, void* stream);
 
+/* Profiling entry points: run only the stages selected by `stage_mask` (bit i = stage i) so a caller
+ * can bracket each kernel with its own CUDA events.  Stages, in order --
+ * forward: 0 clear control, 1 project+SH, 2 scan, 3 emit, 4 tile sort+pack, 5 blend forward;
+ * backward: 0 blend backward, 1 projection backward, 2 pose reduce.
+ * spf_raster_forward / spf_raster_backward are these with every bit set. */
+SPF_API int spf_raster_forward_stages(const SpfRasterDesc* desc, const SpfRasterIn* in, SpfRasterState* st,
+                              SpfRasterOut* out, uint32_t stage_mask, void* stream);
+SPF_API int spf_raster_backward_stages(const SpfRasterDesc* desc, const SpfRasterIn* in, const SpfRasterState* st,
+                               const SpfRasterGradOut* gout, SpfRasterGradIn* gin, uint32_t stage_mask,
+                               void* stream);
+
 /* Debug / parity helper: unpack gaussian ids (point_list) and (tile<<32|depth_bits) keys of the
  * first n slab records into caller buffers (either may be NULL). */
 SPF_API int spf_raster_unpack_sorted(const SpfRasterDesc* desc, const SpfRasterState* st, int64_t n,

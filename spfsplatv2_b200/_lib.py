@@ -52,7 +52,8 @@ class SpfRasterGradIn(C.Structure):
 
 
 EXPORTS = ("spf_version", "spf_last_error", "spf_raster_control_ints", "spf_raster_forward",
-           "spf_raster_backward", "spf_raster_unpack_sorted", "spf_rope2d")
+           "spf_raster_backward", "spf_raster_forward_stages", "spf_raster_backward_stages",
+           "spf_raster_unpack_sorted", "spf_rope2d")
 
 _lib = None
 
@@ -88,6 +89,13 @@ def lib() -> C.CDLL:
     l.spf_raster_backward.restype = C.c_int
     l.spf_raster_backward.argtypes = [C.POINTER(SpfRasterDesc), C.POINTER(SpfRasterIn), C.POINTER(SpfRasterState),
                                       C.POINTER(SpfRasterGradOut), C.POINTER(SpfRasterGradIn), C.c_void_p]
+    l.spf_raster_forward_stages.restype = C.c_int
+    l.spf_raster_forward_stages.argtypes = [C.POINTER(SpfRasterDesc), C.POINTER(SpfRasterIn),
+                                            C.POINTER(SpfRasterState), C.POINTER(SpfRasterOut), C.c_uint32, C.c_void_p]
+    l.spf_raster_backward_stages.restype = C.c_int
+    l.spf_raster_backward_stages.argtypes = [C.POINTER(SpfRasterDesc), C.POINTER(SpfRasterIn),
+                                             C.POINTER(SpfRasterState), C.POINTER(SpfRasterGradOut),
+                                             C.POINTER(SpfRasterGradIn), C.c_uint32, C.c_void_p]
     l.spf_raster_unpack_sorted.restype = C.c_int
     l.spf_raster_unpack_sorted.argtypes = [C.POINTER(SpfRasterDesc), C.POINTER(SpfRasterState), C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_void_p]

@@ -103,6 +103,11 @@ int64_t spf_raster_control_ints(const SpfRasterDesc* desc) {
 
 int spf_raster_forward(const SpfRasterDesc* desc, const SpfRasterIn* in, SpfRasterState* st,
                        SpfRasterOut* out, void* stream) {
+  return spf_raster_forward_stages(desc, in, st, out, 0xffffffffu, stream);
+}
+
+int spf_raster_forward_stages(const SpfRasterDesc* desc, const SpfRasterIn* in, SpfRasterState* st,
+                              SpfRasterOut* out, uint32_t mask, void* stream) {
   int rc;
   if ((rc = check_desc(desc)) || (rc = check_in(desc, in)) || (rc = check_state(st))) return rc;
   if (!out || !out->color || !out->depth) return fail(SPF_ERR_BAD_ARG, "out.color / out.depth must be provided");
@@ -111,19 +116,24 @@ int spf_raster_forward(const SpfRasterDesc* desc, const SpfRasterIn* in, SpfRast
   const spf::ControlLayout cl = spf::control_layout(d.B, d.T, d.NB);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if ((e = cudaMemsetAsync(st->control, 0, (size_t)cl.total * sizeof(int32_t), s)) != cudaSuccess)
+  if ((mask & 1u) && (e = cudaMemsetAsync(st->control, 0, (size_t)cl.total * sizeof(int32_t), s)) != cudaSuccess)
     return cuda_fail(e, "memset(control)");
-  if ((e = spf::launch_project_forward(d, *in, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "project_forward");
-  if ((e = spf::launch_scan(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "scan");
-  if ((e = spf::launch_emit(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "emit");
-  if ((e = spf::launch_tile_sort_pack(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "tile_sort_pack");
-  if ((e = spf::launch_blend_forward(d, *in, *st, *out, s)) != cudaSuccess) return cuda_fail(e, "blend_forward");
+  if ((mask & 2u) && (e = spf::launch_project_forward(d, *in, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "project_forward");
+  if ((mask & 4u) && (e = spf::launch_scan(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "scan");
+  if ((mask & 8u) && (e = spf::launch_emit(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "emit");
+  if ((mask & 16u) && (e = spf::launch_tile_sort_pack(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "tile_sort_pack");
+  if ((mask & 32u) && (e = spf::launch_blend_forward(d, *in, *st, *out, s)) != cudaSuccess) return cuda_fail(e, "blend_forward");
   g_err[0] = 0;
   return SPF_OK;
 }
 
 int spf_raster_backward(const SpfRasterDesc* desc, const SpfRasterIn* in, const SpfRasterState* st,
                         const SpfRasterGradOut* gout, SpfRasterGradIn* gin, void* stream) {
+  return spf_raster_backward_stages(desc, in, st, gout, gin, 0xffffffffu, stream);
+}
+
+int spf_raster_backward_stages(const SpfRasterDesc* desc, const SpfRasterIn* in, const SpfRasterState* st,
+                               const SpfRasterGradOut* gout, SpfRasterGradIn* gin, uint32_t mask, void* stream) {
   int rc;
   if ((rc = check_desc(desc)) || (rc = check_in(desc, in)) || (rc = check_state(st))) return rc;
   if (!gout || !gin) return fail(SPF_ERR_BAD_ARG, "gradient structs must be provided");
@@ -137,8 +147,9 @@ int spf_raster_backward(const SpfRasterDesc* desc, const SpfRasterIn* in, const 
   make_dims(desc, in->sh_coeffs, in->shs != nullptr, d);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if ((e = spf::launch_blend_backward(d, *in, *st, *gout, *gin, s)) != cudaSuccess) return cuda_fail(e, "blend_backward");
-  if ((e = spf::launch_project_backward(d, *in, *st, *gin, s)) != cudaSuccess) return cuda_fail(e, "project_backward");
+  if ((mask & 1u) && (e = spf::launch_blend_backward(d, *in, *st, *gout, *gin, s)) != cudaSuccess) return cuda_fail(e, "blend_backward");
+  if ((mask & 2u) && (e = spf::launch_project_backward(d, *in, *st, *gin, s)) != cudaSuccess) return cuda_fail(e, "project_backward");
+  if ((mask & 4u) && (e = spf::launch_pose_reduce(d, *in, *gin, s)) != cudaSuccess) return cuda_fail(e, "pose_reduce");
   g_err[0] = 0;
   return SPF_OK;
 }

@@ -222,8 +222,10 @@ cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const 
   }
   dim3 grid(d.NB, d.S);
   project_backward_kernel<<<grid, PROJ_THREADS, smem, s>>>(d, in, st, gin);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pose_reduce(const Dims& d, const SpfRasterIn& in, const SpfRasterGradIn& gin, cudaStream_t s) {
   pose_reduce_kernel<<<d.B, 256, 0, s>>>(d, in.viewmatrix, gin.pose_partial, gin.dL_dviewmatrix);
   return cudaGetLastError();
 }

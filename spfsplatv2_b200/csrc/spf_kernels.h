@@ -48,6 +48,7 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
                                   const SpfRasterGradOut& gout, const SpfRasterGradIn& gin, cudaStream_t s);
 cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                     const SpfRasterGradIn& gin, cudaStream_t s);
+cudaError_t launch_pose_reduce(const Dims& d, const SpfRasterIn& in, const SpfRasterGradIn& gin, cudaStream_t s);
 cudaError_t launch_unpack_sorted(const Dims& d, const SpfRasterState& st, int64_t n, int32_t* point_list,
                                  uint64_t* keys, const ControlLayout& cl, cudaStream_t s);
 cudaError_t launch_rope2d(void* tokens, const int64_t* pos, int B, int N, int H, int D, int64_t sb,

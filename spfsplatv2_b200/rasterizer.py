@@ -230,3 +230,58 @@ def unpack_sorted(st: _State):
     L.check(L.lib().spf_raster_unpack_sorted(C.byref(st.desc), C.byref(st.cstate), n, _ptr(pl), _ptr(keys),
                                              _stream(dev)), "spf_raster_unpack_sorted")
     return pl, keys
+
+
+FWD_STAGES = ("clear_control", "project_forward", "scan", "emit", "tile_sort_pack", "blend_forward")
+BWD_STAGES = ("blend_backward", "project_backward", "pose_reduce")
+
+
+def profile_stages(settings: RasterSettings, means, scales, rotations, opacities, shs, colors, viewmatrix,
+                   projmatrix, tanfov, bg, pre_scale, g_color, g_depth, iters: int = 10) -> dict:
+    """Per-kernel device times (ms, mean over ``iters``) measured with CUDA events around each stage of
+    the forward and backward launch sequences (spf_raster_{forward,backward}_stages), on the current
+    stream.  Used by bench.py for the roofline of the dominant kernel."""
+    lib = L.lib()
+    color, depth, alpha, radii, st = forward_with_state(settings, means, scales, rotations, opacities, shs, colors,
+                                                        viewmatrix, projmatrix, tanfov, bg, pre_scale)
+    means_c, scales_c, rots_c, opac_c, shs_c, cols_c = st.keep[:6]
+    dev = means_c.device
+    S, P = means_c.shape[0], means_c.shape[1]
+    B = S * settings.views_per_scene
+    NB = (P + PROJ_THREADS - 1) // PROJ_THREADS
+    f32 = dict(dtype=torch.float32, device=dev)
+    gc, gd = _f32c(g_color), (None if g_depth is None else _f32c(g_depth))
+    gout = L.SpfRasterGradOut(_ptr(gc), _ptr(gd), None)
+    bufs = dict(dup_grad=torch.empty(max(st.n_dups, 1), 12, **f32), pose_partial=torch.empty(B, NB, 16, **f32),
+                d_means=torch.empty_like(means_c), d_scales=torch.empty_like(scales_c), d_rots=torch.empty_like(rots_c),
+                d_opac=torch.empty_like(opac_c), d_shs=None if shs_c is None else torch.empty_like(shs_c),
+                d_cols=None if cols_c is None else torch.empty_like(cols_c), d_view=torch.empty(B, 16, **f32))
+    gin = L.SpfRasterGradIn(_ptr(bufs["dup_grad"]), _ptr(bufs["pose_partial"]), _ptr(bufs["d_means"]),
+                            _ptr(bufs["d_scales"]), _ptr(bufs["d_rots"]), _ptr(bufs["d_opac"]), _ptr(bufs["d_shs"]),
+                            _ptr(bufs["d_cols"]), _ptr(bufs["d_view"]), None)
+    cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
+    stream = _stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    names = [("f", i, n) for i, n in enumerate(FWD_STAGES)] + [("b", i, n) for i, n in enumerate(BWD_STAGES)]
+    acc = {n: 0.0 for _, _, n in names}
+    for it in range(iters + 2):
+        evs = []
+        for kind, i, n in names:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            if kind == "f":
+                rc = lib.spf_raster_forward_stages(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate),
+                                                   C.byref(cout), 1 << i, stream)
+            else:
+                rc = lib.spf_raster_backward_stages(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate),
+                                                    C.byref(gout), C.byref(gin), 1 << i, stream)
+            L.check(rc, n)
+            e1.record(cur)
+            evs.append((n, e0, e1))
+        torch.cuda.synchronize(dev)
+        if it >= 2:
+            for n, e0, e1 in evs:
+                acc[n] += e0.elapsed_time(e1)
+    out = {n: acc[n] / iters for n in acc}
+    out["_n_dups"] = st.n_dups
+    return out

@@ -42,8 +42,11 @@ def _state_forward(sc, no_tma=False, bg=(0.0, 0.0, 0.0)):
     d = _dev()
     b, v = sc.extrinsics.shape[:2]
     h, w = sc.image_shape
-    view, proj, tanfov, scale = camera_setup(sc.extrinsics.reshape(b * v, 4, 4).to(d), sc.intrinsics.reshape(b * v, 3, 3).to(d),
-                                             sc.near.reshape(-1).to(d), sc.far.reshape(-1).to(d), True)
+    # camera matrices on the CPU (exactly the oracle's inputs: a GPU matrix inverse differs by ulps, and the
+    # index parity below is bit-exact), then moved to the device
+    view, proj, tanfov, scale = [x.to(d) for x in camera_setup(
+        sc.extrinsics.reshape(b * v, 4, 4), sc.intrinsics.reshape(b * v, 3, 3), sc.near.reshape(-1),
+        sc.far.reshape(-1), True)]
     K = sc.harmonics.shape[-1]
     s = RasterSettings(h, w, math.isqrt(K) - 1, 1.0, v, sh_layout_ck=True, want_alpha=True, no_tma=no_tma)
     bgt = torch.tensor(bg, dtype=torch.float32, device=d).expand(b * v, 3)
