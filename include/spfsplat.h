@@ -98,6 +98,8 @@ typedef struct {
                                 control[0] = total duplicates N, control[1] = overflow flag */
   uint64_t* bucket;          /* [dup_capacity] (depth_bits<<32 | gaussian) grouped by tile */
   float*    slab;            /* [dup_capacity,12] depth-sorted packed records per tile */
+  float*    cullbox;         /* [dup_capacity,4]  per record: conservative pixel bounding box
+                                (xmin,xmax,ymin,ymax) of the region where alpha >= 1/255 */
   int32_t*  tile_ranges;     /* [B*T,2] start,end into slab */
   float*    final_T;         /* [B,H,W] */
   int32_t*  n_contrib;       /* [B,H,W] */

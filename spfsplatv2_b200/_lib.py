@@ -34,7 +34,7 @@ class SpfRasterIn(C.Structure):
 class SpfRasterState(C.Structure):
     _fields_ = [("xy", _fp), ("depth", _fp), ("conic_opacity", _fp), ("rgb", _fp), ("radii", _fp),
                 ("tiles_touched", _fp), ("dup_offset", _fp), ("control", _fp), ("bucket", _fp), ("slab", _fp),
-                ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp)]
+                ("cullbox", _fp), ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp)]
 
 
 class SpfRasterOut(C.Structure):

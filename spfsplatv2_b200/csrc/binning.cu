@@ -119,6 +119,26 @@ cudaError_t launch_emit(const Dims& d, const SpfRasterState& st, const ControlLa
   return cudaGetLastError();
 }
 
+// Conservative pixel-space bounding box of {alpha >= 1/255}:  o*exp(-q/2) >= 1/255  <=>
+// q = cx dx^2 + 2 cy dx dy + cz dy^2 <= 2 ln(255 o) =: tau.  Half extents of that ellipse are
+// sqrt(tau*cz/det), sqrt(tau*cx/det) with det = cx*cz - cy^2.  Inflated (1e-4 relative + 0.01 px) so
+// rounding can never reject a pixel the exact per-pixel test would accept; a Gaussian that can never
+// reach 1/255 gets an empty box, a degenerate conic an infinite one.
+__device__ __forceinline__ float4 alpha_bbox(float px, float py, float cx, float cy, float cz, float o) {
+  const float inf = __int_as_float(0x7f800000);
+  const float tau = 2.0f * logf(255.0f * o);
+  if (!(tau >= 0.0f)) {
+    if (tau < 0.0f) return make_float4(inf, -inf, inf, -inf);   // never visible
+    return make_float4(-inf, inf, -inf, inf);                   // NaN: do not cull
+  }
+  const float det = cx * cz - cy * cy;
+  if (!(det > 0.0f) || !(cx > 0.0f) || !(cz > 0.0f)) return make_float4(-inf, inf, -inf, inf);
+  const float ex = sqrtf(tau * cz / det) * 1.0001f + 0.01f;
+  const float ey = sqrtf(tau * cx / det) * 1.0001f + 0.01f;
+  if (!(ex < inf) || !(ey < inf)) return make_float4(-inf, inf, -inf, inf);
+  return make_float4(px - ex, px + ex, py - ey, py + ey);
+}
+
 // ---- K5: per-tile sort + slab pack ---------------------------------------------------------------
 // Bitonic network with ascending-only comparators ("flip" then "shift" stages); comparators whose
 // partner index is >= n are skipped, which equals padding with +inf, so any n works.
@@ -187,6 +207,7 @@ tile_sort_pack_kernel(Dims d, SpfRasterState st, const int* __restrict__ tile_st
   }
   const int tx = tile % d.gx, ty = tile / d.gx;
   float4* slab = reinterpret_cast<float4*>(st.slab) + 3 * s64;
+  float4* cull = reinterpret_cast<float4*>(st.cullbox) + s64;
   for (int i = tid; i < n; i += TILE_THREADS) {
     const uint64_t key = sorted[i];
     const int g = (int)(uint32_t)(key & 0xffffffffu);
@@ -201,6 +222,7 @@ tile_sort_pack_kernel(Dims d, SpfRasterState st, const int* __restrict__ tile_st
     slab[3 * i + 0] = make_float4(p.x, p.y, co.x, co.y);
     slab[3 * i + 1] = make_float4(co.z, co.w, r, gg);
     slab[3 * i + 2] = make_float4(b, dep, __int_as_float(slot), __int_as_float(g));
+    cull[i] = alpha_bbox(p.x, p.y, co.x, co.y, co.z, co.w);
   }
 }
 

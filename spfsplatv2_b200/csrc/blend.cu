@@ -1,16 +1,22 @@
 // K6 / K7: per-16x16-tile front-to-back alpha blend (forward) and its backward.
 //
-// One CTA (256 threads, one pixel each; warps own 8x4 pixel blocks) per (view, tile).  The tile's
-// depth-sorted slab -- contiguous 48-byte records {xy, conic, opacity, rgb, depth, slot, id} -- is
-// streamed through a double-buffered shared-memory ring with 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx); every thread then reads each record as three broadcast
-// LDS.128.
+// One CTA (256 threads, one pixel each; every warp owns an 8x4 pixel block) per (view, tile).  The
+// tile's depth-sorted slab -- contiguous 48-byte records {xy, conic, opacity, rgb, depth, slot, id} --
+// and the matching 16-byte alpha bounding boxes are streamed through a double-buffered
+// shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx).
+//
+// Culling: with the encoder's scale law most splats are ~2 px wide, so >90% of (pixel, Gaussian)
+// pairs of a tile are rejections.  Each warp therefore first tests 32 records at a time, one record
+// per LANE, against its 8x4 pixel block (box vs box, conflict-free LDS.128), ballots, and then walks
+// only the set bits with all 32 lanes evaluating their own pixel.  The boxes are conservative
+// (binning.cu: alpha_bbox), the per-pixel test is unchanged, so results are bit-identical to the
+// unculled loop.
 //
 // Backward walks the list back to front (per pixel from its own n_contrib).  Per-Gaussian partial
-// gradients are reduced across the warp with shuffles (skipped when no lane of the warp touches
-// the Gaussian), across the 8 warps through shared memory in a fixed order, and written with ONE
-// plain store per (Gaussian, tile) duplicate into that duplicate's private slot: no atomics,
-// bit-reproducible.
+// gradients (10 floats) are reduced across the warp with a 12-shuffle recursive-halving butterfly
+// (skipped when no lane touches the Gaussian), across the 8 warps through shared memory in a fixed
+// order, and written with ONE plain store per (Gaussian, tile) duplicate into that duplicate's
+// private slot: no atomics anywhere, bit-reproducible.
 //
 // Replaces renderCUDA forward/backward of diff_gauss_pose (SURVEY.md App. B "Blend forward/backward").
 #include "spf_device.cuh"
@@ -19,14 +25,14 @@
 
 namespace spf {
 
-constexpr int CH_F = 128;  // records per forward chunk (6 KB)
+constexpr int CH_F = 128;  // records per forward chunk  (6 KB slab + 2 KB boxes)
 constexpr int CH_B = 64;   // records per backward chunk
 
-__device__ __forceinline__ void pixel_of_thread(int tid, int tile, int gx, int& px, int& py) {
-  const int w = tid >> 5, l = tid & 31;
+__device__ __forceinline__ void warp_block_of_thread(int tid, int tile, int gx, int& bx, int& by) {
+  const int w = tid >> 5;
   const int tx = tile % gx, ty = tile / gx;
-  px = tx * TILE + (w & 1) * 8 + (l & 7);
-  py = ty * TILE + (w >> 1) * 4 + (l >> 3);
+  bx = tx * TILE + (w & 1) * 8;
+  by = ty * TILE + (w >> 1) * 4;
 }
 
 // alpha of one record at one pixel; shared by forward and backward so both make identical
@@ -36,44 +42,53 @@ __device__ __forceinline__ bool eval_alpha(const float4& a, const float4& b, flo
   dx = a.x - pxf;
   dy = a.y - pyf;
   const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-  if (power > 0.0f) return false;
   G = expf(power);
   alpha = fminf(ALPHA_MAX, b.y * G);
-  return alpha >= ALPHA_MIN;
+  return (power <= 0.0f) && (alpha >= ALPHA_MIN);
 }
 
-template <bool TMA, int CH>
-__device__ __forceinline__ void stage_chunk(float4* dst, const float4* __restrict__ src, int cnt,
-                                            uint64_t* bar, int tid) {
+template <bool TMA>
+__device__ __forceinline__ void stage_chunk(float4* dst, float4* dst_box, const float4* __restrict__ src,
+                                            const float4* __restrict__ src_box, int cnt, uint64_t* bar, int tid) {
   if (TMA) {
     if (tid == 0) {
-      mbar_expect_tx(bar, (uint32_t)cnt * 48u);
+      mbar_expect_tx(bar, (uint32_t)cnt * 64u);
       tma_load_1d(dst, src, (uint32_t)cnt * 48u, bar);
+      tma_load_1d(dst_box, src_box, (uint32_t)cnt * 16u, bar);
     }
   } else {
     for (int i = tid; i < cnt * 3; i += TILE_THREADS) dst[i] = src[i];
+    for (int i = tid; i < cnt; i += TILE_THREADS) dst_box[i] = src_box[i];
   }
+}
+
+__device__ __forceinline__ bool box_hits(const float4& bb, float x0, float x1, float y0, float y1) {
+  return (bb.x <= x1) && (bb.y >= x0) && (bb.z <= y1) && (bb.w >= y0);
 }
 
 template <bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS)
 blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterOut out) {
   __shared__ __align__(128) float4 buf[2][CH_F * 3];
+  __shared__ __align__(128) float4 box[2][CH_F];
   __shared__ __align__(8) uint64_t bar[2];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int t = blockIdx.x;
   const int view = t / d.T, tile = t - view * d.T;
   const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
   const int L = e - s;
-  int px, py;
-  pixel_of_thread(tid, tile, d.gx, px, py);
+  int bx, by;
+  warp_block_of_thread(tid, tile, d.gx, bx, by);
+  const int px = bx + (lane & 7), py = by + (lane >> 3);
   const bool inside = (px < d.W) && (py < d.H);
   const float pxf = (float)px, pyf = (float)py;
+  const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
   if (TMA) {
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
   }
   const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
+  const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
   const int nchunks = (L + CH_F - 1) / CH_F;
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
@@ -81,32 +96,43 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   bool done = !inside;
   int pending = -1;  // chunk whose TMA load is in flight beyond the current one
 
-  if (nchunks > 0) stage_chunk<TMA, CH_F>(buf[0], slab, min(CH_F, L), &bar[0], tid);
+  if (nchunks > 0) stage_chunk<TMA>(buf[0], box[0], slab, cull, min(CH_F, L), &bar[0], tid);
   for (int c = 0; c < nchunks; ++c) {
     const int cnt = min(CH_F, L - c * CH_F);
     if (c + 1 < nchunks) {
-      stage_chunk<TMA, CH_F>(buf[(c + 1) & 1], slab + 3 * (size_t)(c + 1) * CH_F,
-                             min(CH_F, L - (c + 1) * CH_F), &bar[(c + 1) & 1], tid);
+      stage_chunk<TMA>(buf[(c + 1) & 1], box[(c + 1) & 1], slab + 3 * (size_t)(c + 1) * CH_F,
+                       cull + (size_t)(c + 1) * CH_F, min(CH_F, L - (c + 1) * CH_F), &bar[(c + 1) & 1], tid);
       pending = c + 1;
     } else {
       pending = -1;
     }
     if (TMA) mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
     else __syncthreads();
-    if (!done) {
+    if (!__all_sync(0xffffffffu, done)) {
       const float4* rec = buf[c & 1];
+      const float4* bb = box[c & 1];
       const int base = c * CH_F;
-      for (int j = 0; j < cnt; ++j) {
-        const float4 a = rec[3 * j], b = rec[3 * j + 1];
-        float dx, dy, G, alpha;
-        if (!eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha)) continue;
-        const float test_T = T * (1.0f - alpha);
-        if (test_T < T_STOP) { done = true; break; }
-        const float4 cc = rec[3 * j + 2];
-        const float w = alpha * T;
-        C0 += b.z * w; C1 += b.w * w; C2 += cc.x * w; D += cc.y * w;
-        T = test_T;
-        last = base + j + 1;
+      for (int g0 = 0; g0 < cnt; g0 += 32) {
+        const int r = g0 + lane;
+        bool hit = false;
+        if (r < cnt) hit = box_hits(bb[r], wx0, wx1, wy0, wy1);
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int j = g0 + __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 a = rec[3 * j], b = rec[3 * j + 1];
+          float dx, dy, G, alpha;
+          bool ok = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && !done;
+          const float test_T = T * (1.0f - alpha);
+          if (ok && test_T < T_STOP) { done = true; ok = false; }
+          if (ok) {
+            const float4 cc = rec[3 * j + 2];
+            const float w = alpha * T;
+            C0 += b.z * w; C1 += b.w * w; C2 += cc.x * w; D += cc.y * w;
+            T = test_T;
+            last = base + j + 1;
+          }
+        }
       }
     }
     if (__syncthreads_and(done)) break;
@@ -139,11 +165,47 @@ cudaError_t launch_blend_forward(const Dims& d, const SpfRasterIn& in, const Spf
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Warp reduction of 10 per-lane values in 12 shuffles (recursive halving).  On return lane L holds,
+// in `out`, the warp total of component  comp_of_lane(L)  (or padding).
+__device__ __forceinline__ float halving_step(float keep_lo, float keep_hi, bool hi, int xor_mask) {
+  const float keep = hi ? keep_hi : keep_lo;
+  const float send = hi ? keep_lo : keep_hi;
+  return keep + __shfl_xor_sync(0xffffffffu, send, xor_mask);
+}
+__device__ __forceinline__ float warp_reduce10(const float v[10], int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+  float u[6];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) u[k] = halving_step(v[k], v[k + 5], h4, 16);
+  u[5] = 0.0f;
+  float w[4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[k] = halving_step(u[k], u[k + 3], h3, 8);
+  w[3] = 0.0f;
+  float x[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) x[k] = halving_step(w[k], w[k + 2], h2, 4);
+  float y = halving_step(x[0], x[1], h1, 2);
+  y += __shfl_xor_sync(0xffffffffu, y, 1);
+  return y;
+}
+// component held by a lane after warp_reduce10, or -1 (padding / duplicate)
+__device__ __forceinline__ int comp_of_lane(int lane) {
+  if (lane & 1) return -1;
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+  const int in3 = 2 * b2 + b1;          // index inside a group of 3 (+1 pad)
+  if (in3 > 2) return -1;
+  const int in5 = 3 * b3 + in3;         // index inside a group of 5 (+1 pad)
+  if (in5 > 4) return -1;
+  return 5 * b4 + in5;
+}
+
 template <bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS)
 blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                       float* __restrict__ dup_grad) {
   __shared__ __align__(128) float4 buf[2][CH_B * 3];
+  __shared__ __align__(128) float4 box[2][CH_B];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ float part[8][CH_B][10];
   __shared__ unsigned long long hitmask[8];
@@ -155,12 +217,15 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
   const int L = e - s;
   if (L == 0) return;
-  int px, py;
-  pixel_of_thread(tid, tile, d.gx, px, py);
+  int bx, by;
+  warp_block_of_thread(tid, tile, d.gx, bx, by);
+  const int px = bx + (lane & 7), py = by + (lane >> 3);
   const bool inside = (px < d.W) && (py < d.H);
   const float pxf = (float)px, pyf = (float)py;
+  const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
   const size_t hw = (size_t)d.H * d.W;
   const size_t pix = (size_t)py * d.W + px;
+  const int mycomp = comp_of_lane(lane);
 
   if (tid == 0) {
     max_contrib_s = 0;
@@ -180,15 +245,14 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
     if (go.dL_ddepth) gd = go.dL_ddepth[(size_t)view * hw + pix];
     if (go.dL_dalpha) ga = go.dL_dalpha[(size_t)view * hw + pix];
   }
-  {
-    int m = ncontrib;
+  int wmax = ncontrib;   // warp-level last contributor
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) atomicMax(&max_contrib_s, m);
-  }
+  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) atomicMax(&max_contrib_s, wmax);
   __syncthreads();
   const int maxc = max_contrib_s;
   const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
+  const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
 
   // duplicates nobody reached: zero gradient records
   for (int i = maxc * 10 + tid; i < L * 10; i += TILE_THREADS) {
@@ -205,32 +269,39 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   float lv0 = 0.f, lv1 = 0.f, lv2 = 0.f, lv3 = 0.f, last_alpha = 0.f;
 
   const int ctop = (maxc - 1) / CH_B;
-  {
-    const int cnt = min(CH_B, maxc - ctop * CH_B);
-    stage_chunk<TMA, CH_B>(buf[0], slab + 3 * (size_t)ctop * CH_B, cnt, &bar[0], tid);
-  }
+  stage_chunk<TMA>(buf[0], box[0], slab + 3 * (size_t)ctop * CH_B, cull + (size_t)ctop * CH_B,
+                   min(CH_B, maxc - ctop * CH_B), &bar[0], tid);
   int it = 0;
   for (int c = ctop; c >= 0; --c, ++it) {
     const int cnt = min(CH_B, maxc - c * CH_B);
     if (c > 0)
-      stage_chunk<TMA, CH_B>(buf[(it + 1) & 1], slab + 3 * (size_t)(c - 1) * CH_B, CH_B, &bar[(it + 1) & 1], tid);
+      stage_chunk<TMA>(buf[(it + 1) & 1], box[(it + 1) & 1], slab + 3 * (size_t)(c - 1) * CH_B,
+                       cull + (size_t)(c - 1) * CH_B, CH_B, &bar[(it + 1) & 1], tid);
     if (TMA) mbar_wait(&bar[it & 1], (uint32_t)((it >> 1) & 1));
     else __syncthreads();
 
     const float4* rec = buf[it & 1];
+    const float4* bb = box[it & 1];
     unsigned long long mymask = 0ull;
-    for (int j = cnt - 1; j >= 0; --j) {
-      const int idx = c * CH_B + j;
-      float v[10];
+    if (c * CH_B < wmax) {   // some pixel of this warp reaches into the chunk
+      for (int g0i = ((cnt - 1) >> 5) << 5; g0i >= 0; g0i -= 32) {
+        const int r = g0i + lane;
+        bool hit = false;
+        if (r < cnt && (c * CH_B + r) < wmax) hit = box_hits(bb[r], wx0, wx1, wy0, wy1);
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int bit = 31 - __clz(mask);
+          mask &= ~(1u << bit);
+          const int j = g0i + bit;
+          const int idx = c * CH_B + j;
+          const float4 a = rec[3 * j], b = rec[3 * j + 1];
+          float dx, dy, G, alpha;
+          const bool contrib = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && (idx < ncontrib);
+          if (!__any_sync(0xffffffffu, contrib)) continue;
+          float v[10];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) v[k] = 0.0f;
-      bool contrib = false;
-      if (idx < ncontrib) {
-        const float4 a = rec[3 * j], b = rec[3 * j + 1];
-        float dx, dy, G, alpha;
-        {
-          if (eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha)) {
-            contrib = true;
+          for (int k = 0; k < 10; ++k) v[k] = 0.0f;
+          if (contrib) {
             const float4 cc = rec[3 * j + 2];
             T = T / (1.0f - alpha);
             const float w = alpha * T;
@@ -254,16 +325,10 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
             v[5] = G * dL_dalpha;
             v[6] = w * g0; v[7] = w * g1; v[8] = w * g2; v[9] = w * gd;
           }
+          const float tot = warp_reduce10(v, lane);
+          if (mycomp >= 0) part[wid][j][mycomp] = tot;
+          mymask |= (1ull << j);
         }
-      }
-      if (__any_sync(0xffffffffu, contrib)) {
-#pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = warp_sum(v[k]);
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < 10; ++k) part[wid][j][k] = v[k];
-        }
-        mymask |= (1ull << j);
       }
     }
     if (lane == 0) hitmask[wid] = mymask;

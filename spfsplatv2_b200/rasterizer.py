@@ -124,9 +124,10 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
         desc.dup_capacity = cap
         t["bucket"] = torch.empty(cap, dtype=torch.int64, device=dev)
         t["slab"] = torch.empty(cap, 12, **f32)
+        t["cullbox"] = torch.empty(cap, 4, **f32)
         cstate = L.SpfRasterState(*[_ptr(t[k]) for k in ("xy", "depth", "conic_opacity", "rgb", "radii",
                                                         "tiles_touched", "dup_offset", "control", "bucket",
-                                                        "slab", "tile_ranges", "final_T", "n_contrib")])
+                                                        "slab", "cullbox", "tile_ranges", "final_T", "n_contrib")])
         cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
         L.check(lib.spf_raster_forward(C.byref(desc), C.byref(cin), C.byref(cstate), C.byref(cout), stream),
                 "spf_raster_forward")
