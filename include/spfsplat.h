@@ -65,6 +65,7 @@ typedef struct {
   uint32_t flags;            /* SPF_FLAG_* */
   float   scale_modifier;    /* settings.scale_modifier */
   int64_t dup_capacity;      /* capacity (records) of bucket / slab / dup_grad buffers */
+  int32_t ticket;            /* written next to N into state.host_counters (see there) */
 } SpfRasterDesc;
 
 /* Inputs (forward kwargs of GaussianRasterizer.__call__, cuda_splatting.py:128-138, batched). */
@@ -103,6 +104,10 @@ typedef struct {
   int32_t*  tile_ranges;     /* [B*T,2] start,end into slab */
   float*    final_T;         /* [B,H,W] */
   int32_t*  n_contrib;       /* [B,H,W] */
+  int32_t*  host_counters;   /* NULL, or 2 int32 of device-mapped PINNED HOST memory: the scan kernel
+                                stores {N, desc.ticket} there (N first, system-scope fence, then the
+                                ticket), so the host learns the duplicate count by polling for its ticket
+                                while the remaining kernels are already queued -- no stream sync. */
 } SpfRasterState;
 
 typedef struct {
@@ -164,6 +169,18 @@ SPF_API int spf_raster_backward_stages(const SpfRasterDesc* desc, const SpfRaste
  * first n slab records into caller buffers (either may be NULL). */
 SPF_API int spf_raster_unpack_sorted(const SpfRasterDesc* desc, const SpfRasterState* st, int64_t n,
                              int32_t* point_list, uint64_t* keys, void* stream);
+
+/* Camera setup of render_cuda (cuda_splatting.py:66-74,84-90; get_fov projection.py:269-283;
+ * get_projection_matrix cuda_splatting.py:15-42) for B views in one launch:
+ *   extrinsics [B,16] camera-to-world (OpenCV), intrinsics [B,9] normalised, near/far [B]  ->
+ *   viewmatrix [B,16] = transpose(inverse(E')), projmatrix [B,16] (transposed), tanfov [B,2],
+ *   pre_scale [B] (= 1/near if scale_invariant else 1; E' has its translation scaled by it).
+ * Backward maps dL/dviewmatrix to dL/dextrinsics (the camera-pose gradient path). */
+SPF_API int spf_camera_forward(int32_t B, int32_t scale_invariant, const float* extrinsics, const float* intrinsics,
+                       const float* near, const float* far, float* viewmatrix, float* projmatrix,
+                       float* tanfov, float* pre_scale, void* stream);
+SPF_API int spf_camera_backward(int32_t B, int32_t scale_invariant, const float* near, const float* viewmatrix,
+                        const float* dL_dviewmatrix, float* dL_dextrinsics, void* stream);
 
 /* 2-D RoPE, in place.  Replaces rope_2d (curope.cpp:49-65).  tokens: [B,N,H,D] view with
  * stride(3)==1, stride(2)==D (kernels.cu:91); positions int64 [B,N,2] contiguous.

@@ -22,7 +22,8 @@ _fp = C.c_void_p
 class SpfRasterDesc(C.Structure):
     _fields_ = [("n_scenes", C.c_int32), ("views_per_scene", C.c_int32), ("n_gaussians", C.c_int32),
                 ("image_height", C.c_int32), ("image_width", C.c_int32), ("sh_degree", C.c_int32),
-                ("flags", C.c_uint32), ("scale_modifier", C.c_float), ("dup_capacity", C.c_int64)]
+                ("flags", C.c_uint32), ("scale_modifier", C.c_float), ("dup_capacity", C.c_int64),
+                ("ticket", C.c_int32)]
 
 
 class SpfRasterIn(C.Structure):
@@ -34,7 +35,7 @@ class SpfRasterIn(C.Structure):
 class SpfRasterState(C.Structure):
     _fields_ = [("xy", _fp), ("depth", _fp), ("conic_opacity", _fp), ("rgb", _fp), ("radii", _fp),
                 ("tiles_touched", _fp), ("dup_offset", _fp), ("control", _fp), ("bucket", _fp), ("slab", _fp),
-                ("cullbox", _fp), ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp)]
+                ("cullbox", _fp), ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp), ("host_counters", _fp)]
 
 
 class SpfRasterOut(C.Structure):
@@ -53,7 +54,7 @@ class SpfRasterGradIn(C.Structure):
 
 EXPORTS = ("spf_version", "spf_last_error", "spf_raster_control_ints", "spf_raster_forward",
            "spf_raster_backward", "spf_raster_forward_stages", "spf_raster_backward_stages",
-           "spf_raster_unpack_sorted", "spf_rope2d")
+           "spf_raster_unpack_sorted", "spf_camera_forward", "spf_camera_backward", "spf_rope2d")
 
 _lib = None
 
@@ -99,6 +100,10 @@ def lib() -> C.CDLL:
     l.spf_raster_unpack_sorted.restype = C.c_int
     l.spf_raster_unpack_sorted.argtypes = [C.POINTER(SpfRasterDesc), C.POINTER(SpfRasterState), C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
+    l.spf_camera_forward.restype = C.c_int
+    l.spf_camera_forward.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 9
+    l.spf_camera_backward.restype = C.c_int
+    l.spf_camera_backward.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5
     l.spf_rope2d.restype = C.c_int
     l.spf_rope2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                              C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p]

@@ -61,3 +61,52 @@ def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tens
     proj = get_projection_matrix(near, far, fov[:, 0], fov[:, 1]).transpose(1, 2)
     view = torch.linalg.inv(extrinsics).transpose(1, 2)
     return view, proj, tanfov, scale
+
+
+class _CameraSetupCUDA(torch.autograd.Function):
+    """camera_setup as ONE kernel (csrc/camera.cu) with the pose-gradient path extrinsics <- viewmatrix."""
+
+    @staticmethod
+    def forward(ctx, extrinsics, intrinsics, near, far, scale_invariant: bool):
+        import ctypes as C
+        from . import _lib as L
+        dev = extrinsics.device
+        B = extrinsics.shape[0]
+        ext = extrinsics.detach().float().contiguous()
+        intr = intrinsics.detach().float().contiguous()
+        nr = near.detach().float().contiguous()
+        fr = far.detach().float().contiguous()
+        view = torch.empty(B, 4, 4, dtype=torch.float32, device=dev)
+        proj = torch.empty(B, 4, 4, dtype=torch.float32, device=dev)
+        tanfov = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        scale = torch.empty(B, dtype=torch.float32, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        L.check(L.lib().spf_camera_forward(B, int(scale_invariant), p(ext), p(intr), p(nr), p(fr), p(view), p(proj),
+                                           p(tanfov), p(scale), stream), "spf_camera_forward")
+        ctx.save_for_backward(nr, view)
+        ctx.scale_invariant = scale_invariant
+        ctx.mark_non_differentiable(proj, tanfov, scale)
+        return view, proj, tanfov, scale
+
+    @staticmethod
+    def backward(ctx, g_view, _gp, _gt, _gs):
+        import ctypes as C
+        from . import _lib as L
+        nr, view = ctx.saved_tensors
+        dev = view.device
+        B = view.shape[0]
+        g = g_view.float().contiguous()
+        d_ext = torch.empty(B, 4, 4, dtype=torch.float32, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        L.check(L.lib().spf_camera_backward(B, int(ctx.scale_invariant), p(nr), p(view), p(g), p(d_ext), stream),
+                "spf_camera_backward")
+        return d_ext, None, None, None, None
+
+
+def camera_setup_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, scale_invariant: bool):
+    """Same outputs as ``camera_setup`` from one kernel launch (CUDA tensors only)."""
+    if not extrinsics.is_cuda:
+        raise RuntimeError("camera_setup_cuda needs CUDA tensors (no CPU fallback on the product path)")
+    return _CameraSetupCUDA.apply(extrinsics, intrinsics, near, far, scale_invariant)

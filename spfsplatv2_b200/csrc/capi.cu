@@ -38,6 +38,7 @@ bool make_dims(const SpfRasterDesc* desc, int sh_coeffs, bool use_sh, spf::Dims&
   d.flags = desc->flags;
   d.mod = desc->scale_modifier;
   d.cap = desc->dup_capacity;
+  d.ticket = desc->ticket;
   (void)sh_coeffs; (void)use_sh;
   return true;
 }
@@ -164,6 +165,29 @@ int spf_raster_unpack_sorted(const SpfRasterDesc* desc, const SpfRasterState* st
   const spf::ControlLayout cl = spf::control_layout(d.B, d.T, d.NB);
   cudaError_t e = spf::launch_unpack_sorted(d, *st, n, point_list, keys, cl, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "unpack_sorted");
+  return SPF_OK;
+}
+
+int spf_camera_forward(int32_t B, int32_t scale_invariant, const float* extrinsics, const float* intrinsics,
+                       const float* near, const float* far, float* viewmatrix, float* projmatrix, float* tanfov,
+                       float* pre_scale, void* stream) {
+  if (B < 1) return fail(SPF_ERR_BAD_ARG, "B must be >= 1");
+  if (!extrinsics || !intrinsics || !near || !far || !viewmatrix || !projmatrix || !tanfov || !pre_scale)
+    return fail(SPF_ERR_BAD_ARG, "spf_camera_forward: NULL pointer");
+  cudaError_t e = spf::launch_camera_forward(B, scale_invariant, extrinsics, intrinsics, near, far, viewmatrix,
+                                             projmatrix, tanfov, pre_scale, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "camera_forward");
+  return SPF_OK;
+}
+
+int spf_camera_backward(int32_t B, int32_t scale_invariant, const float* near, const float* viewmatrix,
+                        const float* dL_dviewmatrix, float* dL_dextrinsics, void* stream) {
+  if (B < 1) return fail(SPF_ERR_BAD_ARG, "B must be >= 1");
+  if (!near || !viewmatrix || !dL_dviewmatrix || !dL_dextrinsics)
+    return fail(SPF_ERR_BAD_ARG, "spf_camera_backward: NULL pointer");
+  cudaError_t e = spf::launch_camera_backward(B, scale_invariant, near, viewmatrix, dL_dviewmatrix, dL_dextrinsics,
+                                              static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "camera_backward");
   return SPF_OK;
 }
 

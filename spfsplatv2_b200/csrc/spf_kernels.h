@@ -34,6 +34,7 @@ struct Dims {
   uint32_t flags;
   float mod;
   int64_t cap;
+  int ticket;
 };
 
 cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
@@ -51,6 +52,11 @@ cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const 
 cudaError_t launch_pose_reduce(const Dims& d, const SpfRasterIn& in, const SpfRasterGradIn& gin, cudaStream_t s);
 cudaError_t launch_unpack_sorted(const Dims& d, const SpfRasterState& st, int64_t n, int32_t* point_list,
                                  uint64_t* keys, const ControlLayout& cl, cudaStream_t s);
+cudaError_t launch_camera_forward(int B, int scale_invariant, const float* ext, const float* intr,
+                                  const float* near, const float* far, float* view, float* proj, float* tanfov,
+                                  float* pre_scale, cudaStream_t s);
+cudaError_t launch_camera_backward(int B, int scale_invariant, const float* near, const float* view,
+                                   const float* d_view, float* d_ext, cudaStream_t s);
 cudaError_t launch_rope2d(void* tokens, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
                           int64_t sn, int dtype, float base, float fwd, cudaStream_t s);
 

@@ -21,7 +21,7 @@ from typing import Literal, Optional
 import torch
 from torch import Tensor, nn
 
-from .camera import camera_setup, get_fov, get_projection_matrix
+from .camera import camera_setup_cuda, get_projection_matrix
 from .rasterizer import RasterSettings, rasterize_batched
 
 DepthRenderingMode = Literal["depth", "log", "disparity", "relative_disparity"]
@@ -71,7 +71,7 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
     With ``views_per_scene = v > 1`` the Gaussian tensors carry B/v scenes and view i reads scene
     i // v (what DecoderSplattingCUDA needs, without materialising v copies)."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
-    view, proj, tanfov, scale = camera_setup(extrinsics, intrinsics, near, far, scale_invariant)
+    view, proj, tanfov, scale = camera_setup_cuda(extrinsics, intrinsics, near, far, scale_invariant)
     return _render_views(view, proj, tanfov, scale if scale_invariant else None, image_shape, background_color,
                          gaussian_means, gaussian_sh_coefficients, gaussian_opacities, gaussian_rotations,
                          gaussian_scales, use_sh, enable_cov_grad, enable_sh_grad, views_per_scene)

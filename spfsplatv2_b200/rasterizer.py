@@ -26,6 +26,17 @@ PROJ_THREADS = 128
 # the blend kernel is already running, and the forward is re-run (rare) if N exceeded the capacity.
 _capacity_hint: dict = {}
 GROWTH = 1.25
+_host_counters: dict = {}     # device index -> (pinned int32[2] tensor, numpy view)
+_ticket = [0]
+
+
+def _counters(dev):
+    hc = _host_counters.get(dev.index)
+    if hc is None:
+        t = torch.zeros(2, dtype=torch.int32).pin_memory()
+        hc = (t, t.numpy())
+        _host_counters[dev.index] = hc
+    return hc
 
 
 def _ptr(t: Optional[Tensor]):
@@ -118,25 +129,34 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     color = torch.empty(B, 3, H, W, **f32)
     depth = torch.empty(B, 1, H, W, **f32)
     alpha = torch.empty(B, 1, H, W, **f32) if s.want_alpha else None
-    host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+    host_t, host_np = _counters(dev)
     stream = _stream(dev)
     while True:
+        _ticket[0] = (_ticket[0] % 0x3fffffff) + 1
+        ticket = _ticket[0]
         desc.dup_capacity = cap
+        desc.ticket = ticket
         t["bucket"] = torch.empty(cap, dtype=torch.int64, device=dev)
         t["slab"] = torch.empty(cap, 12, **f32)
         t["cullbox"] = torch.empty(cap, 4, **f32)
         cstate = L.SpfRasterState(*[_ptr(t[k]) for k in ("xy", "depth", "conic_opacity", "rgb", "radii",
                                                         "tiles_touched", "dup_offset", "control", "bucket",
-                                                        "slab", "cullbox", "tile_ranges", "final_T", "n_contrib")])
+                                                        "slab", "cullbox", "tile_ranges", "final_T", "n_contrib")],
+                                  _ptr(host_t))
         cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
         L.check(lib.spf_raster_forward(C.byref(desc), C.byref(cin), C.byref(cstate), C.byref(cout), stream),
                 "spf_raster_forward")
-        host.copy_(t["control"][:2], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        ev.synchronize()   # waits for the tiny copy only in stream order; all kernels are already enqueued
-        n_dups, overflow = int(host[0]), int(host[1])
-        if n_dups <= cap and not overflow:
+        # The scan kernel stores {N, ticket} into mapped pinned memory; poll for our ticket.  All kernels of
+        # this forward are already queued, so the GPU keeps running emit / sort / blend meanwhile.
+        spins = 0
+        while host_np[1] != ticket:
+            spins += 1
+            if spins > 2_000_000 and (spins & 0xfffff) == 0:
+                torch.cuda.current_stream(dev).synchronize()   # surfaces a launch failure instead of hanging
+                if host_np[1] != ticket:
+                    raise RuntimeError("spf_raster_forward: duplicate count never arrived (kernel failure?)")
+        n_dups = int(host_np[0])
+        if n_dups <= cap:
             break
         cap = int(n_dups * 1.05) + 1024
     _capacity_hint[key] = max(int(n_dups * GROWTH) + 1024, 1024)

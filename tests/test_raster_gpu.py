@@ -228,3 +228,30 @@ def test_shim_matches_batched_path():
         GaussianRasterizer(settings)(means3D=means, means2D=m2d, shs=None, colors_precomp=None,
                                      opacities=sc.opacities[0, :, None].to(d), scales=sc.scales[0].to(d),
                                      rotations=sc.rotations[0].to(d), viewmatrix=view[0])
+
+
+def test_fused_camera_setup_matches_torch_glue():
+    """csrc/camera.cu against the torch restatement of the reference's host glue, values and pose gradient."""
+    from spfsplatv2_b200.camera import camera_setup, camera_setup_cuda
+    d = _dev()
+    torch.manual_seed(3)
+    B = 5
+    q = torch.randn(B, 4); q = q / q.norm(dim=-1, keepdim=True)
+    w, x, y, z = q.unbind(-1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                     2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1).view(B, 3, 3)
+    ext = torch.eye(4).repeat(B, 1, 1); ext[:, :3, :3] = R; ext[:, :3, 3] = torch.randn(B, 3)
+    K = torch.tensor([[0.88, 0, 0.5], [0, 0.91, 0.47], [0, 0, 1.0]]).repeat(B, 1, 1)
+    near = torch.rand(B) + 0.1; far = near * 300
+    for si in (True, False):
+        e_cpu = ext.clone().requires_grad_()
+        ref = camera_setup(e_cpu, K, near, far, si)
+        e_gpu = ext.to(d).requires_grad_()
+        got = camera_setup_cuda(e_gpu, K.to(d), near.to(d), far.to(d), si)
+        for a, b in zip(got, ref):
+            assert torch.allclose(a.cpu(), b, rtol=2e-5, atol=2e-5)
+        wgt = torch.randn(B, 4, 4)
+        (ref[0] * wgt).sum().backward()
+        (got[0] * wgt.to(d)).sum().backward()
+        assert rel_err(e_gpu.grad.cpu(), e_cpu.grad) < 1e-5
