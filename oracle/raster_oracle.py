@@ -86,7 +86,7 @@ class View:
 
 
 def _f(v, like: Tensor) -> Tensor:
-    return torch.tensor(float(v), dtype=torch.float32, device=like.device)
+    return torch.tensor(float(v), dtype=like.dtype, device=like.device)
 
 
 def sh_basis(deg: int, d: Tensor) -> Tensor:
@@ -123,7 +123,7 @@ def preprocess(means: Tensor, scales: Tensor, quats: Tensor, opacities: Tensor,
                quat_order: str = "wxyz") -> dict:
     """Per-Gaussian projection.  fp32, fixed op
     order.  Returns differentiable xy/depth/conic/rgb and integer radius/rect."""
-    assert means.dtype == torch.float32
+    assert means.dtype in (torch.float32, torch.float64)   # float64 only as a truth check for the gradient tests
     V, Pm = view.viewmatrix, view.projmatrix
     mx, my, mz = means[:, 0], means[:, 1], means[:, 2]
 
@@ -225,7 +225,7 @@ def bin_and_sort(pre: dict, view: View):
     gx, gy = view.grid
     rect = pre["rect"].to(torch.int64)
     vis = torch.nonzero(pre["visible"]).flatten()
-    depth_bits = pre["depth"].detach().contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    depth_bits = pre["depth"].detach().float().contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
     keys, vals = [], []
     if vis.numel():
         r = rect[vis]
@@ -270,9 +270,10 @@ def blend(pre: dict, point_list: Tensor, ranges: Tensor, view: View,
     H, W = view.height, view.width
     gx, gy = view.grid
     xy, conic, opac, rgb, depth = pre["xy"], pre["conic"], pre["opacity"], pre["rgb"], pre["depth"]
-    color = torch.zeros(3, H, W, dtype=torch.float32)
-    dimg = torch.zeros(1, H, W, dtype=torch.float32)
-    final_T = torch.ones(H, W, dtype=torch.float32)
+    dt = xy.dtype
+    color = torch.zeros(3, H, W, dtype=dt)
+    dimg = torch.zeros(1, H, W, dtype=dt)
+    final_T = torch.ones(H, W, dtype=dt)
     n_contrib = torch.zeros(H, W, dtype=torch.int32)
     col_tiles, dep_tiles, T_tiles = {}, {}, {}
     for t in range(gx * gy):
@@ -282,8 +283,8 @@ def blend(pre: dict, point_list: Tensor, ranges: Tensor, view: View,
         ty_, tx_ = divmod(t, gx)
         y0, x0 = ty_ * TILE, tx_ * TILE
         y1, x1 = min(y0 + TILE, H), min(x0 + TILE, W)
-        ys = torch.arange(y0, y1, dtype=torch.float32)
-        xs = torch.arange(x0, x1, dtype=torch.float32)
+        ys = torch.arange(y0, y1, dtype=dt)
+        xs = torch.arange(x0, x1, dtype=dt)
         pyy, pxx = torch.meshgrid(ys, xs, indexing="ij")
         pxx, pyy = pxx.reshape(-1), pyy.reshape(-1)
         ids = point_list[s:e].long()
@@ -321,7 +322,7 @@ def blend(pre: dict, point_list: Tensor, ranges: Tensor, view: View,
         color[:, y0:y1, x0:x1] = c_t
         dimg[0, y0:y1, x0:x1] = dep_tiles[t]
         final_T[y0:y1, x0:x1] = T_tiles[t]
-    color = color + final_T[None] * view.bg.reshape(3, 1, 1)
+    color = color + final_T[None] * view.bg.to(dt).reshape(3, 1, 1)
     alpha_img = (1.0 - final_T)[None]
     return color, dimg, alpha_img, final_T, n_contrib
 

@@ -1,0 +1,213 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures under tests/golden/ by running the REFERENCE's own code in this
+container (it cannot travel to the GPU box; the fixtures can).  Test infrastructure only.
+
+    python tests/golden/make_golden.py            # needs /root/reference and oracle/_ref (oracle/build_ref.sh)
+
+Fixtures
+  rope_ref.npz      outputs of the reference's rope_2d_cpu (curope.cpp:11-47, compiled unmodified into
+                    oracle/_ref/curope_ref*.so) and of its pure-PyTorch RoPE2D fallback (pos_embed.py:112-159)
+                    on seeded tokens / positions, forward (+F0) and backward (-F0).
+  decoder_ref.npz   the reference's UNMODIFIED DecoderSplattingCUDA.forward (decoder_splatting_cuda.py:41-78) and
+                    render_cuda (cuda_splatting.py:45-144) driven end to end on a seeded scene, with the external
+                    diff_gauss_pose package (absent) replaced by a recording module whose rasterizer
+                    is oracle/raster_oracle.py.  Holds the inputs, every per-view argument the reference hands to
+                    the rasterizer (viewmatrix, projmatrix, tanfov, bg, scaled means / scales checksums), the
+                    decoder outputs (color, depth) and the gradients of a seeded loss wrt all Gaussian inputs and
+                    the camera extrinsics.  This pins the reference's host glue exactly; the rasterizer arithmetic
+                    itself stays "parity unpinned" (no reference implementation or vectors exist for it).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from typing import NamedTuple
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+
+# ------------------------------------------------------------------------------------------------ RoPE
+def make_rope():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import curope_ref  # the reference's curope.cpp, CPU path
+    # the reference's pure-torch fallback; importing pos_embed tries `.curope` first and falls back on ImportError
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_pos_embed", os.path.join(REF, "src/model/encoder/backbone/croco/pos_embed.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.RoPE2D.__name__ == "RoPE2D" and hasattr(mod.RoPE2D, "apply_rope1d"), "expected the torch fallback"
+
+    out = {}
+    cases = {   # name: (B, N, H, D, max_pos, base)
+        "small": (2, 7, 3, 16, 5, 100.0),
+        "d8": (1, 5, 2, 8, 40, 100.0),            # Q=2: scalar path of the kernel
+        "vit": (2, 37, 12, 64, 16, 100.0),        # decoder head shape (12 heads x 64), 16x16 patch grid
+        "enc": (1, 20, 16, 64, 16, 100.0),        # encoder head shape
+        "base10k": (1, 9, 2, 32, 30, 10000.0),
+    }
+    g = torch.Generator().manual_seed(0)
+    for name, (B, N, H, D, mp, base) in cases.items():
+        tok = torch.randn(B, N, H, D, generator=g)
+        pos = torch.randint(0, mp, (B, N, 2), generator=g, dtype=torch.int64)
+        fwd = tok.clone()
+        curope_ref.rope_2d(fwd, pos, base, 1.0)
+        bwd = tok.clone()
+        curope_ref.rope_2d(bwd, pos, base, -1.0)
+        rt = fwd.clone()
+        curope_ref.rope_2d(rt, pos, base, -1.0)
+        py = mod.RoPE2D(freq=base, F0=1.0)(tok.transpose(1, 2).clone(), pos).transpose(1, 2).contiguous()
+        out[f"{name}_tokens"] = tok.numpy()
+        out[f"{name}_pos"] = pos.numpy()
+        out[f"{name}_base"] = np.float32(base)
+        out[f"{name}_fwd"] = fwd.numpy()
+        out[f"{name}_bwd"] = bwd.numpy()
+        out[f"{name}_pytorch_fwd"] = py.numpy()
+        print(f"rope {name}: cpp-vs-pytorch max|d| = {(fwd - py).abs().max():.2e}, round trip {(rt - tok).abs().max():.2e}")
+    np.savez_compressed(os.path.join(HERE, "rope_ref.npz"), **out)
+
+
+# --------------------------------------------------------------------------------------------- decoder
+def _stub_modules():
+    import torchvision  # noqa: F401  (real one first)
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            t = type(name, (), {"__init__": lambda self, *a, **k: None})
+            setattr(self, name, t)
+            return t
+
+    for name in ("dacite", "lightning", "lightning.pytorch", "skvideo", "skvideo.io", "matplotlib",
+                 "matplotlib.figure", "omegaconf", "pytorch3d", "pytorch3d.transforms", "lightning.pytorch.loggers",
+                 "lightning.pytorch.loggers.wandb", "lightning.pytorch.utilities", "lightning.pytorch.callbacks",
+                 "lightning.pytorch.plugins.environments", "lightning.pytorch.plugins", "matplotlib.pyplot",
+                 "matplotlib.cm", "matplotlib.colors", "lpips", "plyfile", "wandb", "colorspacious", "moviepy",
+                 "moviepy.editor", "hydra", "skimage", "skimage.metrics", "roma", "e3nn", "timm"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                m = _Any(name)
+                m.__path__ = []
+                sys.modules[name] = m
+
+
+RECORD = []
+
+
+def _fake_diff_gauss_pose():
+    from oracle import raster_oracle as O
+
+    class GaussianRasterizationSettings(NamedTuple):
+        image_height: int
+        image_width: int
+        tanfovx: float
+        tanfovy: float
+        bg: torch.Tensor
+        scale_modifier: float
+        projmatrix: torch.Tensor
+        sh_degree: int
+        prefiltered: bool
+        debug: bool
+        enable_cov_grad: bool
+        enable_sh_grad: bool
+
+    class GaussianRasterizer(torch.nn.Module):
+        def __init__(self, raster_settings):
+            super().__init__()
+            self.s = raster_settings
+
+        def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                    cov3Ds_precomp=None, viewmatrix=None):
+            s = self.s
+            RECORD.append(dict(
+                tanfov=(s.tanfovx, s.tanfovy), tanfov_types=(type(s.tanfovx).__name__, type(s.tanfovy).__name__),
+                bg=s.bg.detach().clone(), projmatrix=s.projmatrix.detach().clone(), viewmatrix=viewmatrix.detach().clone(),
+                proj_contiguous=s.projmatrix.is_contiguous(), sh_degree=s.sh_degree, hw=(s.image_height, s.image_width),
+                means_sum=means3D.detach().double().sum().item(), scales_sum=scales.detach().double().sum().item(),
+                shs_shape=None if shs is None else tuple(shs.shape), opac_shape=tuple(opacities.shape),
+                flags=(s.prefiltered, s.debug, s.enable_cov_grad, s.enable_sh_grad, s.scale_modifier)))
+            vw = O.View(s.image_height, s.image_width, float(s.tanfovx), float(s.tanfovy), s.bg,
+                        viewmatrix.contiguous(), s.projmatrix.contiguous(), s.sh_degree, s.scale_modifier)
+            r = O.render(means3D, scales, rotations, opacities.reshape(-1), shs, colors_precomp, vw)
+            return r["color"], r["depth"], None, r["alpha"], r["pre"]["radius"], None
+
+    m = types.ModuleType("diff_gauss_pose")
+    m.GaussianRasterizationSettings = GaussianRasterizationSettings
+    m.GaussianRasterizer = GaussianRasterizer
+    return m
+
+
+def make_decoder():
+    _stub_modules()
+    sys.modules["diff_gauss_pose"] = _fake_diff_gauss_pose()
+    sys.path.insert(0, REF)
+    from src.model.decoder import get_decoder
+    from src.model.decoder.decoder_splatting_cuda import DecoderSplattingCUDACfg
+    from src.model.types import Gaussians
+    from spfsplatv2_b200.synthetic import make_batch
+
+    b, v, h, w = 2, 2, 64, 48
+    bg = [0.2, 0.1, 0.4]
+    sc = make_batch(b, seed=31, v_cxt=1, h=h, w=w, grid=(24, 24), regime="trained", n_target=v, with_cov=True)
+    # vary near per view and use an off-centre principal point so the glue's handling of both is pinned
+    sc.near = torch.tensor([[0.5, 0.8], [0.3, 1.0]])
+    sc.far = sc.near * 1000.0
+    sc.intrinsics = sc.intrinsics.clone()
+    sc.intrinsics[1, :, 0, 2] = 0.47
+    sc.intrinsics[1, :, 1, 1] = 0.91
+    leaves = {k: getattr(sc, k).clone().requires_grad_() for k in
+              ("means", "rotations", "scales", "harmonics", "opacities", "extrinsics")}
+    dec = get_decoder(DecoderSplattingCUDACfg("splatting_cuda", bg, True, True, True))
+    g = Gaussians(leaves["means"], sc.covariances, leaves["rotations"], leaves["scales"], leaves["harmonics"],
+                  leaves["opacities"])
+    out = dec.forward(g, leaves["extrinsics"], sc.intrinsics, sc.near, sc.far, (h, w))
+    gen = torch.Generator().manual_seed(1)
+    wc = torch.randn(b, v, 3, h, w, generator=gen)
+    wd = 0.05 * torch.randn(b, v, h, w, generator=gen)
+    loss = (out.color * wc).sum() + (out.depth * wd).sum()
+    loss.backward()
+    assert len(RECORD) == b * v
+    assert all(r["tanfov_types"] == ("float", "float") for r in RECORD)
+    fx = dict(
+        bg=np.array(bg, np.float32), image_shape=np.array([h, w]),
+        means=sc.means.numpy(), rotations=sc.rotations.numpy(), scales=sc.scales.numpy(),
+        harmonics=sc.harmonics.numpy(), opacities=sc.opacities.numpy(), extrinsics=sc.extrinsics.numpy(),
+        intrinsics=sc.intrinsics.numpy(), near=sc.near.numpy(), far=sc.far.numpy(),
+        wc=wc.numpy(), wd=wd.numpy(), loss=np.float64(loss.item()),
+        color=out.color.detach().numpy(), depth=out.depth.detach().numpy(),
+        rec_viewmatrix=torch.stack([r["viewmatrix"] for r in RECORD]).numpy(),
+        rec_projmatrix=torch.stack([r["projmatrix"] for r in RECORD]).numpy(),
+        rec_tanfov=np.array([r["tanfov"] for r in RECORD], np.float64),
+        rec_bg=torch.stack([r["bg"] for r in RECORD]).numpy(),
+        rec_means_sum=np.array([r["means_sum"] for r in RECORD]),
+        rec_scales_sum=np.array([r["scales_sum"] for r in RECORD]),
+        rec_proj_contiguous=np.array([r["proj_contiguous"] for r in RECORD]),
+        rec_sh_degree=np.array([r["sh_degree"] for r in RECORD]),
+        rec_shs_shape=np.array([r["shs_shape"] for r in RECORD]),
+        rec_opac_shape=np.array([r["opac_shape"] for r in RECORD]),
+    )
+    for k, t in leaves.items():
+        fx["grad_" + k] = t.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "decoder_ref.npz"), **fx)
+    print(f"decoder: {len(RECORD)} rasterizer calls, loss {loss.item():.6f}, color mean {out.color.mean().item():.4f}; "
+          f"proj contiguous={RECORD[0]['proj_contiguous']}, shs {RECORD[0]['shs_shape']}, opac {RECORD[0]['opac_shape']}")
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        raise SystemExit("make_golden.py needs /root/reference (run it in the build container)")
+    make_rope()
+    make_decoder()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
