@@ -40,6 +40,8 @@ def rope_2d(tokens: torch.Tensor, positions: torch.Tensor, base: float, fwd: flo
         raise RuntimeError(f"unsupported dtype {tokens.dtype}")
     if positions.dtype != torch.int64:
         raise RuntimeError("positions must be int64")
+    if tokens.numel() == 0:
+        return
     stream = C.c_void_p(torch.cuda.current_stream(tokens.device).cuda_stream)
     with torch.cuda.device(tokens.device):
         rc = L.lib().spf_rope2d(C.c_void_p(tokens.data_ptr()), C.c_void_p(positions.data_ptr()), B, N, H, D,

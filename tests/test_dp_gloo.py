@@ -1,0 +1,86 @@
+"""world_size-2 `gloo` tests (CPU) of the data-parallel host logic (spfsplatv2_b200/dp.py): view sharding and the
+one gradient all-reduce per step.  The renderer stand-in is the CPU oracle -- the test exercises the plumbing, the
+CUDA path is covered by the `-m gpu` tests and bench.py --gpus N."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spfsplatv2_b200.dp import GradAllReduce, render_views_sharded, shard_indices
+
+
+def test_shard_indices_partition_ragged_and_empty():
+    for n, world in [(16, 2), (7, 4), (3, 8), (0, 2), (8, 8)]:
+        parts = [shard_indices(n, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert shard_indices(3, 5, 8) == []
+    with pytest.raises(ValueError):
+        shard_indices(4, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _scene_and_views(n_views):
+    from spfsplatv2_b200.synthetic import make_scene
+    return make_scene(seed=41, v_cxt=1, h=32, w=32, grid=(10, 10), regime="trained", n_target=n_views)
+
+
+def _render_fns(sc, leaves):
+    from oracle import raster_oracle as O
+    from spfsplatv2_b200.camera import camera_setup
+    h, w = sc.image_shape
+    view, proj, tanfov, scale = camera_setup(sc.extrinsics[0], sc.intrinsics[0], sc.near[0], sc.far[0], True)
+    wts = torch.randn(sc.extrinsics.shape[1], 3, h, w, generator=torch.Generator().manual_seed(5))
+
+    def render_view(i):
+        vw = O.View(h, w, float(tanfov[i, 0]), float(tanfov[i, 1]), torch.zeros(3), view[i].contiguous(), proj[i].contiguous(), 4, 1.0)
+        return O.render(leaves["means"] * scale[i], leaves["scales"] * scale[i], leaves["rotations"], leaves["opacities"],
+                        leaves["harmonics"].permute(0, 2, 1).contiguous(), None, vw)["color"]
+
+    def loss_of_view(i, color):
+        return (color * wts[i]).sum()
+    return render_view, loss_of_view
+
+
+def _leaves(sc):
+    return {k: getattr(sc, k)[0].clone().requires_grad_() for k in ("means", "scales", "rotations", "opacities", "harmonics")}
+
+
+def _worker(rank, world, port, n_views, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        sc = _scene_and_views(n_views)
+        leaves = _leaves(sc)
+        rv, lv = _render_fns(sc, leaves)
+        red = GradAllReduce(torch.device("cpu"))
+        grads = render_views_sharded(rv, lv, n_views, leaves, red)
+        torch.save({k: v for k, v in grads.items()}, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_views", [3, 1])     # ragged (2+1) and "rank 1 has nothing to render"
+def test_sharded_views_allreduce_equals_single_process(tmp_path, n_views):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n_views, str(tmp_path)), nprocs=world, join=True)
+    sc = _scene_and_views(n_views)
+    leaves = _leaves(sc)
+    rv, lv = _render_fns(sc, leaves)
+    total = sum(lv(i, rv(i)) for i in range(n_views))
+    total.backward()
+    got = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
+    for k, t in leaves.items():
+        for r in range(world):
+            assert torch.allclose(got[r][k], t.grad, rtol=1e-5, atol=1e-6 * float(t.grad.abs().max())), (k, r)
+        assert torch.equal(got[0][k], got[1][k])          # every rank ends with the same reduced gradient
+    assert got[0]["_loss"].item() == pytest.approx(total.item(), rel=1e-5)
