@@ -17,11 +17,22 @@
 
 namespace spf {
 
-__global__ void __launch_bounds__(PROJ_THREADS)
+// MULTI = several views per scene: SH gradients accumulate over views in a second shared-memory buffer.
+// !MULTI (training: one target view per scene): the SH gradient overwrites the staged SH input IN PLACE, so a
+// block needs 38.4 KB instead of 76.8 KB of shared memory (5 resident blocks per SM instead of 2).
+//
+// Staging: the block's 128 SH rows are one contiguous 38.4 KB span in HBM (both [K,3] and [3,K] layouts), so
+// when it is 16-B aligned one thread moves it with a single 1-D TMA bulk copy (cp.async.bulk + mbarrier) and
+// the whole block meanwhile sums the duplicate records and runs the geometry backward; the SH gradient goes
+// back the same way (bulk store).  Odd row length (75 floats at degree 4) makes the per-thread rows
+// bank-conflict free without padding.  Unaligned / even-row cases use cooperative 128-bit copies.
+template <bool MULTI>
+__global__ void __launch_bounds__(PROJ_THREADS, MULTI ? 2 : 5)
 project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGradIn gin) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   __shared__ ViewConsts vc;
   __shared__ float pose_warp[PROJ_THREADS / 32][15];
+  __shared__ __align__(8) uint64_t bar;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int scene = blockIdx.y;
@@ -29,18 +40,35 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
   const int g = g0 + tid;
   const int nvalid = min(PROJ_THREADS, d.P - g0);
   const int row = 3 * in.sh_coeffs;
-  const int stride = (row & 1) ? row : row + 1;
-  float* sh_s = smem;                             // input SH  [128][stride]
-  float* dsh_s = smem + PROJ_THREADS * stride;    // SH grads  [128][stride]
   const bool use_sh = in.shs != nullptr;
   const bool ck = (d.flags & SPF_FLAG_SH_LAYOUT_CK) != 0;
   const bool cov_grad = !(d.flags & SPF_FLAG_NO_COV_GRAD);
   const bool sh_grad = !(d.flags & SPF_FLAG_NO_SH_GRAD);
+  const int sk = ck ? 1 : 3, sc = ck ? in.sh_coeffs : 1;
+
+  // block-uniform: can the SH rows move by TMA?
+  const size_t row_off = ((size_t)scene * d.P + g0) * row;
+  const uint32_t bytes = (uint32_t)nvalid * row * 4u;
+  const bool tma = use_sh && (row & 1) && ((bytes & 15u) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(in.shs) + row_off * 4) & 15) == 0) &&
+                   (gin.dL_dshs == nullptr || ((reinterpret_cast<uintptr_t>(gin.dL_dshs) + row_off * 4) & 15) == 0);
+  const int stride = ((row & 1) || tma) ? row : row + 1;
+  float* sh_s = smem;                                            // input SH  [128][stride]
+  float* dsh_s = MULTI ? smem + PROJ_THREADS * stride : smem;    // SH grads  [128][stride] (in place if !MULTI)
 
   if (use_sh) {
-    const float* src = in.shs + ((size_t)scene * d.P + g0) * row;
-    block_copy_g2s(sh_s, src, nvalid * row, row, stride, tid, PROJ_THREADS);
-    for (int i = tid; i < PROJ_THREADS * stride; i += PROJ_THREADS) dsh_s[i] = 0.0f;
+    if (tma) {
+      if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, bytes);
+        tma_load_1d(sh_s, in.shs + row_off, bytes, &bar);
+      }
+    } else {
+      block_copy_g2s(sh_s, in.shs + row_off, nvalid * row, row, stride, tid, PROJ_THREADS);
+    }
+    if (MULTI)
+      for (int i = tid; i < PROJ_THREADS * stride; i += PROJ_THREADS) dsh_s[i] = 0.0f;
   }
 
   const size_t sg = (size_t)scene * d.P + g;
@@ -55,12 +83,35 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
 
   for (int vi = 0; vi < d.v; ++vi) {
     const int view = scene * d.v + vi;
-    __syncthreads();   // previous view's vc / pose_warp fully consumed; SH staging complete
+    // issue this view's per-Gaussian loads before the barrier so their latency overlaps the camera setup
+    const size_t vg = (size_t)view * d.P + g;
+    int tiles = 0, off = 0;
+    float3 rgbv = make_float3(0.f, 0.f, 0.f);
+    if (g < d.P) {
+      tiles = st.tiles_touched[vg];
+      off = st.dup_offset[vg];
+      if (use_sh) rgbv = make_float3(st.rgb[vg * 3], st.rgb[vg * 3 + 1], st.rgb[vg * 3 + 2]);
+    }
+    __syncthreads();   // previous view's vc / pose_warp fully consumed; mbarrier init / plain SH staging visible
     if (tid == 0) {
       float V[16], Pm[16], bg[3];
       for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[view * 16 + i]; Pm[i] = in.projmatrix[view * 16 + i]; }
       for (int i = 0; i < 3; ++i) bg[i] = in.bg[view * 3 + i];
       make_view_consts(vc, V, Pm, in.tanfov[view * 2], in.tanfov[view * 2 + 1], bg, d.mod, d.W, d.H);
+    }
+    // sum this Gaussian's duplicate records (contiguous slots) while thread 0 builds the view constants
+    float a[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a[k] = 0.0f;
+    if (tiles > 0) {
+      const float4* rec = reinterpret_cast<const float4*>(gin.dup_grad) + 3 * (size_t)off;
+      for (int j = 0; j < tiles; ++j) {
+        const float4 r0 = rec[3 * j], r1 = rec[3 * j + 1];
+        const float2 r2 = *reinterpret_cast<const float2*>(rec + 3 * j + 2);
+        a[0] += r0.x; a[1] += r0.y; a[2] += r0.z; a[3] += r0.w;
+        a[4] += r1.x; a[5] += r1.y; a[6] += r1.z; a[7] += r1.w;
+        a[8] += r2.x; a[9] += r2.y;
+      }
     }
     __syncthreads();
     const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
@@ -73,20 +124,7 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
 #pragma unroll
     for (int i = 0; i < 9; ++i) o.dA[i] = 0.f;
 
-    const size_t vg = (size_t)view * d.P + g;
-    const int tiles = (g < d.P) ? st.tiles_touched[vg] : 0;
     if (tiles > 0) {
-      // sum this Gaussian's duplicate records (contiguous slots)
-      float a[10];
-#pragma unroll
-      for (int k = 0; k < 10; ++k) a[k] = 0.0f;
-      const float4* rec = reinterpret_cast<const float4*>(gin.dup_grad) + 3 * (size_t)st.dup_offset[vg];
-      for (int j = 0; j < tiles; ++j) {
-        const float4 r0 = rec[3 * j], r1 = rec[3 * j + 1], r2 = rec[3 * j + 2];
-        a[0] += r0.x; a[1] += r0.y; a[2] += r0.z; a[3] += r0.w;
-        a[4] += r1.x; a[5] += r1.y; a[6] += r1.z; a[7] += r1.w;
-        a[8] += r2.x; a[9] += r2.y;
-      }
       Grad2D g2;
       g2.dpx = a[0]; g2.dpy = a[1]; g2.dconx = a[2]; g2.dcony = a[3]; g2.dconz = a[4];
       g2.dopacity = a[5]; g2.drgb[0] = a[6]; g2.drgb[1] = a[7]; g2.drgb[2] = a[8]; g2.ddepth = a[9];
@@ -95,46 +133,39 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
         float* o2 = gin.dL_dmeans2D + vg * 3;
         o2[0] = g2.dpx * 0.5f * vc.Wf; o2[1] = g2.dpy * 0.5f * vc.Hf; o2[2] = 0.0f;
       }
-      float m[3] = {m_in[0] * ps, m_in[1] * ps, m_in[2] * ps};
-      float s[3] = {s_in[0] * ps, s_in[1] * ps, s_in[2] * ps};
-      float gdir[3] = {0.f, 0.f, 0.f};
+      const float m[3] = {m_in[0] * ps, m_in[1] * ps, m_in[2] * ps};
+      const float s[3] = {s_in[0] * ps, s_in[1] * ps, s_in[2] * ps};
+      project_backward_geom(vc, m, s, q, g2, cov_grad, o);
       if (use_sh) {
         const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
         const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-        const float x = dx * inv, y = dy * inv, z = dz * inv;
-        float Bk[MAX_SH_COEFFS], vk[MAX_SH_COEFFS];
-        sh_basis(d.deg, x, y, z, Bk);
-        const float* mysh = sh_s + tid * stride;
-        float* mydsh = dsh_s + tid * stride;
-        float gm[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float acc = 0.0f;
-          for (int k = 0; k < d.K; ++k) acc += Bk[k] * (ck ? mysh[c * in.sh_coeffs + k] : mysh[k * 3 + c]);
-          gm[c] = (acc + 0.5f) < 0.0f ? 0.0f : g2.drgb[c];   // clamp mask
-        }
-        for (int k = 0; k < d.K; ++k) {
-          float vv = 0.0f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int idx = ck ? (c * in.sh_coeffs + k) : (k * 3 + c);
-            mydsh[idx] += Bk[k] * gm[c];
-            vv += mysh[idx] * gm[c];
-          }
-          vk[k] = vv;
-        }
-        if (sh_grad) sh_basis_backward(d.deg, x, y, z, vk, gdir[0], gdir[1], gdir[2]);
+        // clamp mask saved by the forward in the sign bit of rgb (-0.0f <=> SH colour was negative before the clamp)
+        const float gm[3] = {(__float_as_uint(rgbv.x) >> 31) ? 0.0f : g2.drgb[0],
+                             (__float_as_uint(rgbv.y) >> 31) ? 0.0f : g2.drgb[1],
+                             (__float_as_uint(rgbv.z) >> 31) ? 0.0f : g2.drgb[2]};
+        if (tma) mbar_wait(&bar, 0);
+        float gdir[3];
+        sh_backward_fused<MULTI>(d.deg, dx * inv, dy * inv, dz * inv, sh_s + tid * stride, dsh_s + tid * stride, sk, sc,
+                                 gm, gdir[0], gdir[1], gdir[2]);
+        if (sh_grad) view_dir_backward(vc, m, gdir, o);
       } else {
         dcol[0] += g2.drgb[0]; dcol[1] += g2.drgb[1]; dcol[2] += g2.drgb[2];
       }
-      project_backward(vc, m, s, q, g2, gdir, cov_grad, o);
 #pragma unroll
       for (int i = 0; i < 3; ++i) { dm[i] += o.dm[i] * ps; ds[i] += o.ds[i] * ps; }
 #pragma unroll
       for (int i = 0; i < 4; ++i) dq[i] += o.dq[i];
-    } else if (g < d.P && gin.dL_dmeans2D) {
-      float* o2 = gin.dL_dmeans2D + vg * 3;
-      o2[0] = 0.f; o2[1] = 0.f; o2[2] = 0.f;
+    } else {
+      if (g < d.P && gin.dL_dmeans2D) {
+        float* o2 = gin.dL_dmeans2D + vg * 3;
+        o2[0] = 0.f; o2[1] = 0.f; o2[2] = 0.f;
+      }
+      if (use_sh && !MULTI) {
+        // in-place mode: a Gaussian that contributes nothing must still hand back a zero SH gradient
+        if (tma) mbar_wait(&bar, 0);
+        float* mydsh = dsh_s + tid * stride;
+        for (int i = 0; i < row; ++i) mydsh[i] = 0.0f;
+      }
     }
 
     // pose contribution: 15 floats, warp shuffle -> block -> partial[view][block]
@@ -168,9 +199,19 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
       for (int i = 0; i < 3; ++i) gin.dL_dcolors[sg * 3 + i] = dcol[i];
   }
   if (use_sh && gin.dL_dshs) {
-    __syncthreads();
-    float* dst = gin.dL_dshs + ((size_t)scene * d.P + g0) * row;
-    block_copy_s2g(dst, dsh_s, nvalid * row, row, stride, tid, PROJ_THREADS);
+    float* dst = gin.dL_dshs + row_off;
+    if (tma) {
+      fence_proxy_async();     // generic-proxy writes of dsh_s -> visible to the bulk-copy (async) proxy
+      __syncthreads();
+      if (tid == 0) {
+        tma_store_1d(dst, dsh_s, bytes);
+        tma_store_commit();
+        tma_store_wait_all();  // shared memory must stay valid until the copy engine has read it
+      }
+    } else {
+      __syncthreads();
+      block_copy_s2g(dst, dsh_s, nvalid * row, row, stride, tid, PROJ_THREADS);
+    }
   }
 }
 
@@ -210,19 +251,25 @@ pose_reduce_kernel(Dims d, const float* __restrict__ viewmatrix, const float* __
   }
 }
 
-cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
-                                    const SpfRasterGradIn& gin, cudaStream_t s) {
+template <bool MULTI>
+static cudaError_t launch_pb(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st, const SpfRasterGradIn& gin,
+                             cudaStream_t s) {
   const int row = 3 * in.sh_coeffs;
   const int stride = (row & 1) ? row : row + 1;
-  const size_t smem = in.shs ? (size_t)2 * PROJ_THREADS * stride * sizeof(float) : 0;
+  const size_t smem = in.shs ? (size_t)(MULTI ? 2 : 1) * PROJ_THREADS * stride * sizeof(float) : 0;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(project_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(project_backward_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
   }
   dim3 grid(d.NB, d.S);
-  project_backward_kernel<<<grid, PROJ_THREADS, smem, s>>>(d, in, st, gin);
+  project_backward_kernel<MULTI><<<grid, PROJ_THREADS, smem, s>>>(d, in, st, gin);
   return cudaGetLastError();
+}
+
+cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                    const SpfRasterGradIn& gin, cudaStream_t s) {
+  return d.v > 1 ? launch_pb<true>(d, in, st, gin, s) : launch_pb<false>(d, in, st, gin, s);
 }
 
 cudaError_t launch_pose_reduce(const Dims& d, const SpfRasterIn& in, const SpfRasterGradIn& gin, cudaStream_t s) {

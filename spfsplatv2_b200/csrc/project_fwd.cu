@@ -17,8 +17,9 @@ namespace spf {
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
                        int* __restrict__ block_sum) {
-  extern __shared__ __align__(16) float sh_s[];
+  extern __shared__ __align__(128) float sh_s[];
   __shared__ ViewConsts vc;
+  __shared__ __align__(8) uint64_t bar;
   __shared__ int warp_tot[PROJ_THREADS / 32];
 
   const int tid = threadIdx.x;
@@ -29,34 +30,51 @@ project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restric
   const int nvalid = min(PROJ_THREADS, d.P - g0);
   const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
 
+  // SH staging: the block's rows are one contiguous span; when it is 16-B aligned and the row length is odd
+  // (bank-conflict free without padding) ONE thread moves it with a 1-D TMA bulk copy and the projection math
+  // below overlaps the transfer; otherwise cooperative 128-bit loads.
+  const int row = 3 * in.sh_coeffs;
+  const size_t row_off = ((size_t)scene * d.P + g0) * row;
+  const uint32_t bytes = (uint32_t)nvalid * row * 4u;
+  const bool tma = in.shs && (row & 1) && ((bytes & 15u) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(in.shs) + row_off * 4) & 15) == 0);
+  const int stride = ((row & 1) || tma) ? row : row + 1;
+  if (in.shs) {
+    if (tma) {
+      if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, bytes);
+        tma_load_1d(sh_s, in.shs + row_off, bytes, &bar);
+      }
+    } else {
+      block_copy_g2s(sh_s, in.shs + row_off, nvalid * row, row, stride, tid, PROJ_THREADS);
+    }
+  }
+  // per-Gaussian loads are issued before the barrier so their latency overlaps thread 0's camera setup
+  const size_t sg = (size_t)scene * d.P + min(g, d.P - 1);
+  const size_t vg = (size_t)view * d.P + g;
+  float m[3], s[3], q[4];
+  for (int i = 0; i < 3; ++i) {
+    m[i] = __ldg(in.means3D + sg * 3 + i) * ps;
+    s[i] = __ldg(in.scales + sg * 3 + i) * ps;
+  }
+  {
+    const float4 qq = __ldg(reinterpret_cast<const float4*>(in.rotations) + sg);
+    if (d.flags & SPF_FLAG_QUAT_XYZW) { q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z; }
+    else { q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w; }
+  }
+  const float opac = __ldg(in.opacities + sg);
   if (tid == 0) {
     float V[16], Pm[16], bg[3];
     for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[view * 16 + i]; Pm[i] = in.projmatrix[view * 16 + i]; }
     for (int i = 0; i < 3; ++i) bg[i] = in.bg[view * 3 + i];
     make_view_consts(vc, V, Pm, in.tanfov[view * 2], in.tanfov[view * 2 + 1], bg, d.mod, d.W, d.H);
   }
-  const int row = 3 * in.sh_coeffs;
-  const int stride = (row & 1) ? row : row + 1;
-  if (in.shs) {
-    const float* src = in.shs + ((size_t)scene * d.P + g0) * row;
-    block_copy_g2s(sh_s, src, nvalid * row, row, stride, tid, PROJ_THREADS);
-  }
   __syncthreads();
 
   int tiles = 0;
   if (g < d.P) {
-    const size_t sg = (size_t)scene * d.P + g;
-    const size_t vg = (size_t)view * d.P + g;
-    float m[3], s[3], q[4];
-    for (int i = 0; i < 3; ++i) {
-      m[i] = __ldg(in.means3D + sg * 3 + i) * ps;
-      s[i] = __ldg(in.scales + sg * 3 + i) * ps;
-    }
-    {
-      const float4 qq = __ldg(reinterpret_cast<const float4*>(in.rotations) + sg);
-      if (d.flags & SPF_FLAG_QUAT_XYZW) { q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z; }
-      else { q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w; }
-    }
     Projected o;
     const bool vis = project_forward(vc, m, s, q, o);
     tiles = o.tiles;
@@ -65,15 +83,16 @@ project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restric
     if (in.shs) {
       const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
       const float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
-      float Bk[MAX_SH_COEFFS];
-      sh_basis(d.deg, dx * inv, dy * inv, dz * inv, Bk);
-      const float* mysh = sh_s + tid * stride;
+      if (tma) mbar_wait(&bar, 0);
       const bool ck = (d.flags & SPF_FLAG_SH_LAYOUT_CK) != 0;
+      float pre[3];
+      sh_eval_fused(d.deg, dx * inv, dy * inv, dz * inv, sh_s + tid * stride, ck ? 1 : 3, ck ? in.sh_coeffs : 1, pre);
+      // clamp at 0; a channel that was negative is stored as -0.0f: it blends like 0, and its sign bit is the
+      // clamp mask projection-backward needs (so it never re-evaluates the SH sum)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float acc = 0.0f;
-        for (int k = 0; k < d.K; ++k) acc += Bk[k] * (ck ? mysh[c * in.sh_coeffs + k] : mysh[k * 3 + c]);
-        rgb[c] = fmaxf(acc + 0.5f, 0.0f);
+        const float p5 = pre[c] + 0.5f;
+        rgb[c] = (p5 < 0.0f) ? -0.0f : p5;
       }
     } else {
       for (int c = 0; c < 3; ++c) rgb[c] = __ldg(in.colors_precomp + sg * 3 + c);
@@ -82,7 +101,7 @@ project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restric
     reinterpret_cast<float2*>(st.xy)[vg] = make_float2(o.px, o.py);
     st.depth[vg] = o.depth;
     reinterpret_cast<float4*>(st.conic_opacity)[vg] =
-        make_float4(o.conx, o.cony, o.conz, __ldg(in.opacities + sg));
+        make_float4(o.conx, o.cony, o.conz, opac);
     st.rgb[vg * 3 + 0] = rgb[0]; st.rgb[vg * 3 + 1] = rgb[1]; st.rgb[vg * 3 + 2] = rgb[2];
     st.radii[vg] = o.radius;
     st.tiles_touched[vg] = o.tiles;

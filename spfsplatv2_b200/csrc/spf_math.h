@@ -244,6 +244,103 @@ SPF_HD void sh_basis_backward(int deg, float x, float y, float z, const float* v
   gx += SH_C4_8 * 4.0f * x * (xx - 3.0f * yy) * v[24];  gy += SH_C4_8 * 4.0f * y * (yy - 3.0f * xx) * v[24];
 }
 
+// SH colour of one Gaussian without a basis array: rgb[c] = sum_k B_k(x,y,z) * sh[k*sk + c*sc]  (explicit fmaf so the
+// colour path keeps fused multiply-adds even in the -fmad=false translation unit; not index-affecting).
+SPF_HD void sh_eval_fused(int deg, float x, float y, float z, const float* sh, int sk, int sc, float rgb[3]) {
+  float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+#define SPF_SH_EVAL(k, B)                                                                  \
+  {                                                                                        \
+    const float b_ = (B);                                                                  \
+    const int i_ = (k) * sk;                                                               \
+    r0 = fmaf(b_, sh[i_], r0); r1 = fmaf(b_, sh[i_ + sc], r1); r2 = fmaf(b_, sh[i_ + 2 * sc], r2); \
+  }
+  SPF_SH_EVAL(0, SH_C0)
+  if (deg >= 1) {
+    SPF_SH_EVAL(1, -SH_C1 * y) SPF_SH_EVAL(2, SH_C1 * z) SPF_SH_EVAL(3, -SH_C1 * x)
+    if (deg >= 2) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      SPF_SH_EVAL(4, SH_C2_0 * xy) SPF_SH_EVAL(5, SH_C2_1 * yz) SPF_SH_EVAL(6, SH_C2_2 * (2.0f * zz - xx - yy))
+      SPF_SH_EVAL(7, SH_C2_3 * xz) SPF_SH_EVAL(8, SH_C2_4 * (xx - yy))
+      if (deg >= 3) {
+        SPF_SH_EVAL(9, SH_C3_0 * y * (3.0f * xx - yy)) SPF_SH_EVAL(10, SH_C3_1 * xy * z)
+        SPF_SH_EVAL(11, SH_C3_2 * y * (4.0f * zz - xx - yy))
+        SPF_SH_EVAL(12, SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy))
+        SPF_SH_EVAL(13, SH_C3_4 * x * (4.0f * zz - xx - yy)) SPF_SH_EVAL(14, SH_C3_5 * z * (xx - yy))
+        SPF_SH_EVAL(15, SH_C3_6 * x * (xx - 3.0f * yy))
+        if (deg >= 4) {
+          SPF_SH_EVAL(16, SH_C4_0 * xy * (xx - yy)) SPF_SH_EVAL(17, SH_C4_1 * yz * (3.0f * xx - yy))
+          SPF_SH_EVAL(18, SH_C4_2 * xy * (7.0f * zz - 1.0f)) SPF_SH_EVAL(19, SH_C4_3 * yz * (7.0f * zz - 3.0f))
+          SPF_SH_EVAL(20, SH_C4_4 * (zz * (35.0f * zz - 30.0f) + 3.0f)) SPF_SH_EVAL(21, SH_C4_5 * xz * (7.0f * zz - 3.0f))
+          SPF_SH_EVAL(22, SH_C4_6 * (xx - yy) * (7.0f * zz - 1.0f)) SPF_SH_EVAL(23, SH_C4_7 * xz * (xx - 3.0f * yy))
+          SPF_SH_EVAL(24, SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy)))
+        }
+      }
+    }
+  }
+#undef SPF_SH_EVAL
+  rgb[0] = r0; rgb[1] = r1; rgb[2] = r2;
+}
+
+// Fused single pass over the SH coefficients for the backward (no Bk[] / vk[] arrays => few live registers):
+// for every k:  b = B_k(x,y,z);  v = sum_c sh[k,c]*gm[c];  dsh[k,c] (+)= b*gm[c];  (gx,gy,gz) += v * dB_k/d(x,y,z).
+// Element (k,c) of sh / dsh lives at  k*sk + c*sc  (sk=3,sc=1 for [K,3]; sk=1,sc=Kstore for [3,K]).
+// dsh may alias sh (each element is read before it is written).  gm = dL/drgb with the clamp mask applied.
+template <bool ACCUM>
+SPF_HD void sh_backward_fused(int deg, float x, float y, float z, const float* sh, float* dsh, int sk, int sc,
+                              const float gm[3], float& gx, float& gy, float& gz) {
+  gx = gy = gz = 0.0f;
+#define SPF_SH_TERM(k, B, DX, DY, DZ)                                                      \
+  {                                                                                        \
+    const float b_ = (B);                                                                  \
+    const int i_ = (k) * sk;                                                               \
+    const float v_ = (sh[i_] * gm[0] + sh[i_ + sc] * gm[1]) + sh[i_ + 2 * sc] * gm[2];     \
+    if (ACCUM) { dsh[i_] += b_ * gm[0]; dsh[i_ + sc] += b_ * gm[1]; dsh[i_ + 2 * sc] += b_ * gm[2]; } \
+    else { dsh[i_] = b_ * gm[0]; dsh[i_ + sc] = b_ * gm[1]; dsh[i_ + 2 * sc] = b_ * gm[2]; } \
+    gx += v_ * (DX); gy += v_ * (DY); gz += v_ * (DZ);                                     \
+  }
+  SPF_SH_TERM(0, SH_C0, 0.0f, 0.0f, 0.0f)
+  if (deg < 1) return;
+  SPF_SH_TERM(1, -SH_C1 * y, 0.0f, -SH_C1, 0.0f)
+  SPF_SH_TERM(2, SH_C1 * z, 0.0f, 0.0f, SH_C1)
+  SPF_SH_TERM(3, -SH_C1 * x, -SH_C1, 0.0f, 0.0f)
+  if (deg < 2) return;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  SPF_SH_TERM(4, SH_C2_0 * xy, SH_C2_0 * y, SH_C2_0 * x, 0.0f)
+  SPF_SH_TERM(5, SH_C2_1 * yz, 0.0f, SH_C2_1 * z, SH_C2_1 * y)
+  SPF_SH_TERM(6, SH_C2_2 * (2.0f * zz - xx - yy), SH_C2_2 * -2.0f * x, SH_C2_2 * -2.0f * y, SH_C2_2 * 4.0f * z)
+  SPF_SH_TERM(7, SH_C2_3 * xz, SH_C2_3 * z, 0.0f, SH_C2_3 * x)
+  SPF_SH_TERM(8, SH_C2_4 * (xx - yy), SH_C2_4 * 2.0f * x, SH_C2_4 * -2.0f * y, 0.0f)
+  if (deg < 3) return;
+  SPF_SH_TERM(9, SH_C3_0 * y * (3.0f * xx - yy), SH_C3_0 * 6.0f * xy, SH_C3_0 * 3.0f * (xx - yy), 0.0f)
+  SPF_SH_TERM(10, SH_C3_1 * xy * z, SH_C3_1 * yz, SH_C3_1 * xz, SH_C3_1 * xy)
+  SPF_SH_TERM(11, SH_C3_2 * y * (4.0f * zz - xx - yy), SH_C3_2 * -2.0f * xy, SH_C3_2 * (4.0f * zz - xx - 3.0f * yy),
+              SH_C3_2 * 8.0f * yz)
+  SPF_SH_TERM(12, SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), SH_C3_3 * -6.0f * xz, SH_C3_3 * -6.0f * yz,
+              SH_C3_3 * (6.0f * zz - 3.0f * xx - 3.0f * yy))
+  SPF_SH_TERM(13, SH_C3_4 * x * (4.0f * zz - xx - yy), SH_C3_4 * (4.0f * zz - 3.0f * xx - yy), SH_C3_4 * -2.0f * xy,
+              SH_C3_4 * 8.0f * xz)
+  SPF_SH_TERM(14, SH_C3_5 * z * (xx - yy), SH_C3_5 * 2.0f * xz, SH_C3_5 * -2.0f * yz, SH_C3_5 * (xx - yy))
+  SPF_SH_TERM(15, SH_C3_6 * x * (xx - 3.0f * yy), SH_C3_6 * 3.0f * (xx - yy), SH_C3_6 * -6.0f * xy, 0.0f)
+  if (deg < 4) return;
+  SPF_SH_TERM(16, SH_C4_0 * xy * (xx - yy), SH_C4_0 * (3.0f * xx * y - yy * y), SH_C4_0 * (xx * x - 3.0f * x * yy), 0.0f)
+  SPF_SH_TERM(17, SH_C4_1 * yz * (3.0f * xx - yy), SH_C4_1 * 6.0f * xy * z, SH_C4_1 * 3.0f * z * (xx - yy),
+              SH_C4_1 * y * (3.0f * xx - yy))
+  SPF_SH_TERM(18, SH_C4_2 * xy * (7.0f * zz - 1.0f), SH_C4_2 * y * (7.0f * zz - 1.0f), SH_C4_2 * x * (7.0f * zz - 1.0f),
+              SH_C4_2 * 14.0f * xy * z)
+  SPF_SH_TERM(19, SH_C4_3 * yz * (7.0f * zz - 3.0f), 0.0f, SH_C4_3 * z * (7.0f * zz - 3.0f),
+              SH_C4_3 * y * (21.0f * zz - 3.0f))
+  SPF_SH_TERM(20, SH_C4_4 * (zz * (35.0f * zz - 30.0f) + 3.0f), 0.0f, 0.0f, SH_C4_4 * z * (140.0f * zz - 60.0f))
+  SPF_SH_TERM(21, SH_C4_5 * xz * (7.0f * zz - 3.0f), SH_C4_5 * z * (7.0f * zz - 3.0f), 0.0f,
+              SH_C4_5 * x * (21.0f * zz - 3.0f))
+  SPF_SH_TERM(22, SH_C4_6 * (xx - yy) * (7.0f * zz - 1.0f), SH_C4_6 * 2.0f * x * (7.0f * zz - 1.0f),
+              SH_C4_6 * -2.0f * y * (7.0f * zz - 1.0f), SH_C4_6 * 14.0f * z * (xx - yy))
+  SPF_SH_TERM(23, SH_C4_7 * xz * (xx - 3.0f * yy), SH_C4_7 * 3.0f * z * (xx - yy), SH_C4_7 * -6.0f * xy * z,
+              SH_C4_7 * x * (xx - 3.0f * yy))
+  SPF_SH_TERM(24, SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy)), SH_C4_8 * 4.0f * x * (xx - 3.0f * yy),
+              SH_C4_8 * 4.0f * y * (yy - 3.0f * xx), 0.0f)
+#undef SPF_SH_TERM
+}
+
 // Upstream 2-D gradients of one Gaussian in one view (what blend-backward reduces).
 struct Grad2D {
   float dpx, dpy;             // dL/d(pixel-space mean)
@@ -268,9 +365,8 @@ struct Grad3D {
 //           or SH direction gradients are disabled)
 //   cov_grad : include the covariance path's contribution to means and pose.
 // All outputs are ACCUMULATED (+=) so one Gaussian can sum several views.
-SPF_HD void project_backward(const ViewConsts& vc, const float m[3], const float s[3],
-                             const float q[4], const Grad2D& g, const float g_dir[3],
-                             bool cov_grad, Grad3D& out) {
+SPF_HD void project_backward_geom(const ViewConsts& vc, const float m[3], const float s[3],
+                                  const float q[4], const Grad2D& g, bool cov_grad, Grad3D& out) {
   const float* V = vc.V;
   const float* P = vc.P;
   const float tx = V[0] * m[0] + V[4] * m[1] + V[8] * m[2] + V[12];
@@ -389,18 +485,26 @@ SPF_HD void project_backward(const ViewConsts& vc, const float m[3], const float
   }
   for (int j = 0; j < 3; ++j) out.dtau[j] += gt[j];
 
-  // view direction: dir = d/|d|, d = m - campos
-  {
-    const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
-    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-    const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
-    const float dot = nx * g_dir[0] + ny * g_dir[1] + nz * g_dir[2];
-    const float gd0 = (g_dir[0] - nx * dot) * inv;
-    const float gd1 = (g_dir[1] - ny * dot) * inv;
-    const float gd2 = (g_dir[2] - nz * dot) * inv;
-    out.dm[0] += gd0; out.dm[1] += gd1; out.dm[2] += gd2;
-    out.dcam[0] -= gd0; out.dcam[1] -= gd1; out.dcam[2] -= gd2;
-  }
+}
+
+// Backward of the SH view direction  dir = d/|d|, d = m - campos : g_dir = dL/d(dir) (from the SH basis).
+SPF_HD void view_dir_backward(const ViewConsts& vc, const float m[3], const float g_dir[3], Grad3D& out) {
+  const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
+  const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+  const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
+  const float dot = nx * g_dir[0] + ny * g_dir[1] + nz * g_dir[2];
+  const float gd0 = (g_dir[0] - nx * dot) * inv;
+  const float gd1 = (g_dir[1] - ny * dot) * inv;
+  const float gd2 = (g_dir[2] - nz * dot) * inv;
+  out.dm[0] += gd0; out.dm[1] += gd1; out.dm[2] += gd2;
+  out.dcam[0] -= gd0; out.dcam[1] -= gd1; out.dcam[2] -= gd2;
+}
+
+SPF_HD void project_backward(const ViewConsts& vc, const float m[3], const float s[3],
+                             const float q[4], const Grad2D& g, const float g_dir[3],
+                             bool cov_grad, Grad3D& out) {
+  project_backward_geom(vc, m, s, q, g, cov_grad, out);
+  view_dir_backward(vc, m, g_dir, out);
 }
 
 // campos_i = -sum_j tau_j A_ij  =>  fold dL/dcampos into dL/dA and dL/dtau.

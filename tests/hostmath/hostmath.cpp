@@ -36,12 +36,10 @@ void hm_sh_forward(int P, int deg, const float* means, const float* V, const flo
     const float* m = means + 3 * g;
     float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
     float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
-    float B[25];
-    sh_basis(deg, dx * inv, dy * inv, dz * inv, B);
+    float pre[3];
+    sh_eval_fused(deg, dx * inv, dy * inv, dz * inv, shs + (size_t)g * K * 3, 3, 1, pre);
     for (int c = 0; c < 3; ++c) {
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k) acc += B[k] * shs[(size_t)g * K * 3 + k * 3 + c];
-      acc += 0.5f;
+      float acc = pre[c] + 0.5f;
       rgb[3 * g + c] = acc < 0.f ? 0.f : acc;
     }
   }
@@ -78,15 +76,11 @@ void hm_project_backward(int P, int deg, int use_sh, int cov_grad, int sh_grad,
         for (int k = 0; k < K; ++k) acc += B[k] * shs[(size_t)g * K * 3 + k * 3 + c];
         gm[c] = (acc + 0.5f) < 0.f ? 0.f : g2.drgb[c];
       }
-      for (int k = 0; k < K; ++k) {
-        float vk = 0.f;
-        for (int c = 0; c < 3; ++c) {
-          dshs[(size_t)g * K * 3 + k * 3 + c] = B[k] * gm[c];
-          vk += shs[(size_t)g * K * 3 + k * 3 + c] * gm[c];
-        }
-        v[k] = vk;
-      }
-      if (sh_grad) sh_basis_backward(deg, x, y, z, v, gdir[0], gdir[1], gdir[2]);
+      // the fused single-pass SH backward the CUDA kernel uses (dsh written, dL/ddir accumulated)
+      float gx, gy, gz;
+      sh_backward_fused<false>(deg, x, y, z, shs + (size_t)g * K * 3, dshs + (size_t)g * K * 3, 3, 1, gm, gx, gy, gz);
+      if (sh_grad) { gdir[0] = gx; gdir[1] = gy; gdir[2] = gz; }
+      (void)v;
     }
     Grad3D o = {};
     project_backward(vc, m, scales + 3 * g, quats + 4 * g, g2, gdir, cov_grad != 0, o);
