@@ -51,7 +51,9 @@ enum {
   SPF_FLAG_NO_SH_GRAD   = 1u << 2, /* settings.enable_sh_grad == False */
   SPF_FLAG_NO_TMA       = 1u << 3, /* debugging: stage the slab with plain loads instead of cp.async.bulk */
   SPF_FLAG_QUAT_XYZW    = 1u << 4, /* rotations are (x,y,z,w); default (w,x,y,z) */
-  SPF_FLAG_DEPTH_NORMALIZED = 1u << 5 /* reserved (depth / alpha); not implemented */
+  SPF_FLAG_DEPTH_NORMALIZED = 1u << 5, /* reserved (depth / alpha); not implemented */
+  SPF_FLAG_BWD_V1       = 1u << 6  /* debugging / cross-check: the first-generation blend backward (back to front,
+                                      per-record warp butterfly) instead of the pair-compaction kernel */
 };
 
 /* Problem description; mirrors GaussianRasterizationSettings (cuda_splatting.py:105-120). */
@@ -104,6 +106,8 @@ typedef struct {
   int32_t*  tile_ranges;     /* [B*T,2] start,end into slab */
   float*    final_T;         /* [B,H,W] */
   int32_t*  n_contrib;       /* [B,H,W] */
+  float*    accum;           /* [B,H,W,4] blended sums (rgb, depth) WITHOUT the background term; written by
+                                forward, read by backward (16-byte aligned) */
   int32_t*  host_counters;   /* NULL, or 2 int32 of device-mapped PINNED HOST memory: the scan kernel
                                 stores {N, desc.ticket} there (N first, system-scope fence, then the
                                 ticket), so the host learns the duplicate count by polling for its ticket

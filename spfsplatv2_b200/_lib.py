@@ -15,6 +15,7 @@ SPF_FLAG_NO_COV_GRAD = 1 << 1
 SPF_FLAG_NO_SH_GRAD = 1 << 2
 SPF_FLAG_NO_TMA = 1 << 3
 SPF_FLAG_QUAT_XYZW = 1 << 4
+SPF_FLAG_BWD_V1 = 1 << 6
 
 _fp = C.c_void_p
 
@@ -35,7 +36,7 @@ class SpfRasterIn(C.Structure):
 class SpfRasterState(C.Structure):
     _fields_ = [("xy", _fp), ("depth", _fp), ("conic_opacity", _fp), ("rgb", _fp), ("radii", _fp),
                 ("tiles_touched", _fp), ("dup_offset", _fp), ("control", _fp), ("bucket", _fp), ("slab", _fp),
-                ("cullbox", _fp), ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp), ("host_counters", _fp)]
+                ("cullbox", _fp), ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp), ("accum", _fp), ("host_counters", _fp)]
 
 
 class SpfRasterOut(C.Structure):

@@ -151,6 +151,9 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
     if (out.alpha) out.alpha[(size_t)view * hw + pix] = 1.0f - T;
     st.final_T[(size_t)view * hw + pix] = T;
     st.n_contrib[(size_t)view * hw + pix] = last;
+    // private copy of the blended sums (no background term): backward derives every pixel's total
+    // sum_j q_j w_j from it, independent of what the caller does with its output tensors afterwards
+    reinterpret_cast<float4*>(st.accum)[(size_t)view * hw + pix] = make_float4(C0, C1, C2, D);
   }
 }
 
@@ -202,7 +205,7 @@ __device__ __forceinline__ int comp_of_lane(int lane) {
 
 template <bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS)
-blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
+blend_backward_v1_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                       float* __restrict__ dup_grad) {
   __shared__ __align__(128) float4 buf[2][CH_B * 3];
   __shared__ __align__(128) float4 box[2][CH_B];
@@ -347,13 +350,253 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Blend backward, v2: front-to-back traversal with per-warp PAIR COMPACTION.
+//
+// ncu on v1 (profiles/r1_summary_baseline.md): a warp walks ~57 box-hit records per tile, but on average
+// only 4 of its 32 pixels actually receive a contribution from a hit record, and the 130-instruction
+// gradient + butterfly body ran at 4/32 lane efficiency.  v2 splits the work:
+//
+//   test phase  (per hit record, all 32 lanes = pixels, same ~45-instruction alpha test as the forward):
+//       contributing lanes update their running transmittance T and prefix P = sum_{j<=i} q_j w_j
+//       (q_j = rgb_j . dL/dC + depth_j dL/dD, w_j = alpha_j T_j) and push one 16-byte pair record
+//       {pixel, record, G, T_before, P_after} into the warp's ring queue in shared memory
+//       (ballot + popc compaction; pairs of one record are adjacent, in lane order).
+//   dense phase (whenever 32 pairs are queued): ONE PAIR PER LANE.  With the closed form
+//       dL/dalpha_i = T_i q_i - (Qtot - P_i) / (1 - alpha_i),   Qtot = sum_j q_j w_j + T_final (bg.dL/dC - dL/dA)
+//       every pair is independent, so all 32 lanes do useful gradient math; a segmented shuffle reduction
+//       over runs of equal record (early exit at the longest run) leaves each record's 10 partial sums in
+//       its run-head lane, which accumulates them into part[warp][record].
+//   per chunk   : fixed-order cross-warp sum of part[] and ONE plain store per (Gaussian, tile) duplicate.
+//
+// Still no atomics and a fixed summation order: bit-reproducible run to run.  Front-to-back order also removes
+// v1's T reconstruction by repeated division.
+constexpr int CH_B2 = 128;   // records per backward chunk
+constexpr int QCAP = 64;     // pair-queue ring capacity per warp (power of two, >= 63)
+
+struct BwdSmem {
+  float4 rec[2][CH_B2 * 3];
+  float4 box[2][CH_B2];
+  uint4 queue[8][QCAP];
+  float part[8][CH_B2][10];
+  float4 pg[TILE_THREADS];    // per pixel: dL/dC (3), dL/dD
+  float pq[TILE_THREADS];     // per pixel: Qtot
+  uint64_t bar[2];
+  int max_contrib;
+};
+
+template <bool TMA>
+__global__ void __launch_bounds__(TILE_THREADS, 3)
+blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
+                      float* __restrict__ dup_grad) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t = blockIdx.x;
+  const int view = t / d.T, tile = t - view * d.T;
+  const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
+  const int L = e - s;
+  if (L == 0) return;
+  int bx, by;
+  warp_block_of_thread(tid, tile, d.gx, bx, by);
+  const int px = bx + (lane & 7), py = by + (lane >> 3);
+  const bool inside = (px < d.W) && (py < d.H);
+  const float pxf = (float)px, pyf = (float)py;
+  const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
+  const size_t hw = (size_t)d.H * d.W;
+  const size_t pix = (size_t)py * d.W + px;
+
+  if (tid == 0) {
+    S.max_contrib = 0;
+    if (TMA) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
+  }
+  __syncthreads();
+
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, gd = 0.f, qtot = 0.f;
+  int ncontrib = 0;
+  if (inside) {
+    ncontrib = st.n_contrib[(size_t)view * hw + pix];
+    float ga = 0.f;
+    if (go.dL_dcolor) {
+      const float* gc = go.dL_dcolor + (size_t)view * 3 * hw;
+      g0 = gc[pix]; g1 = gc[hw + pix]; g2 = gc[2 * hw + pix];
+    }
+    if (go.dL_ddepth) gd = go.dL_ddepth[(size_t)view * hw + pix];
+    if (go.dL_dalpha) ga = go.dL_dalpha[(size_t)view * hw + pix];
+    const float4 acc = reinterpret_cast<const float4*>(st.accum)[(size_t)view * hw + pix];
+    const float* bg = bg_all + view * 3;
+    const float bgdot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2 - ga;
+    qtot = (acc.x * g0 + acc.y * g1) + (acc.z * g2 + acc.w * gd) + st.final_T[(size_t)view * hw + pix] * bgdot;
+  }
+  S.pg[tid] = make_float4(g0, g1, g2, gd);
+  S.pq[tid] = qtot;
+  int wmax = ncontrib;   // warp-level last contributor
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) atomicMax(&S.max_contrib, wmax);
+  __syncthreads();
+  const int maxc = S.max_contrib;
+  const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
+  const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
+
+  // duplicates nobody reached: zero gradient records
+  for (int i = maxc * 10 + tid; i < L * 10; i += TILE_THREADS) {
+    const int r = i / 10, k = i - r * 10;
+    const int slot = __float_as_int(__ldg(reinterpret_cast<const float*>(slab + 3 * r + 2) + 2));
+    dup_grad[(size_t)slot * 12 + k] = 0.0f;
+  }
+  if (maxc == 0) return;
+
+  float T = 1.0f, P = 0.0f;
+  uint4* q = S.queue[wid];
+  float (*part)[10] = S.part[wid];
+  const float4* pgw = S.pg + wid * 32;
+  const float* pqw = S.pq + wid * 32;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int qhead = 0, qcount = 0;
+
+  const int nchunks = (maxc + CH_B2 - 1) / CH_B2;
+  stage_chunk<TMA>(S.rec[0], S.box[0], slab, cull, min(CH_B2, maxc), &S.bar[0], tid);
+  for (int c = 0; c < nchunks; ++c) {
+    const int cnt = min(CH_B2, maxc - c * CH_B2);
+    if (c + 1 < nchunks)
+      stage_chunk<TMA>(S.rec[(c + 1) & 1], S.box[(c + 1) & 1], slab + 3 * (size_t)(c + 1) * CH_B2,
+                       cull + (size_t)(c + 1) * CH_B2, min(CH_B2, maxc - (c + 1) * CH_B2), &S.bar[(c + 1) & 1], tid);
+    // zero this warp's partial sums for the chunk's records (128-bit stores)
+    {
+      float4* p4 = reinterpret_cast<float4*>(&part[0][0]);
+      const int n4 = (cnt * 10 + 3) >> 2;
+      for (int i = lane; i < n4; i += 32) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (TMA) mbar_wait(&S.bar[c & 1], (uint32_t)((c >> 1) & 1));
+    else __syncthreads();
+    __syncwarp();
+
+    const float4* rec = S.rec[c & 1];
+    const float4* bb = S.box[c & 1];
+    const int base = c * CH_B2;
+
+    // dense phase over the first n queued pairs (n <= 32)
+    auto dense = [&](int n) {
+      int j = -1;
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] = 0.0f;
+      if (lane < n) {
+        const uint4 en = q[(qhead + lane) & (QCAP - 1)];
+        j = (int)(en.x & 0xffffu);
+        const int pl = (int)(en.x >> 16);
+        const float G = __uint_as_float(en.y), Tb = __uint_as_float(en.z), Pa = __uint_as_float(en.w);
+        const float4 a = rec[3 * j], b = rec[3 * j + 1], cc = rec[3 * j + 2];
+        const float4 g = pgw[pl];
+        const float dx = a.x - (float)(bx + (pl & 7)), dy = a.y - (float)(by + (pl >> 3));
+        const float alpha = fminf(ALPHA_MAX, b.y * G);
+        const float qv = (b.z * g.x + b.w * g.y) + (cc.x * g.z + cc.y * g.w);
+        const float dL_dalpha = Tb * qv - __fdividef(pqw[pl] - Pa, 1.0f - alpha);
+        const float dL_dG = b.y * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
+        v[1] = dL_dG * (-gdy * b.x - gdx * a.w);
+        v[2] = -0.5f * gdx * dx * dL_dG;
+        v[3] = -gdx * dy * dL_dG;
+        v[4] = -0.5f * gdy * dy * dL_dG;
+        v[5] = G * dL_dalpha;
+        const float w = alpha * Tb;
+        v[6] = w * g.x; v[7] = w * g.y; v[8] = w * g.z; v[9] = w * g.w;
+      }
+      // segmented reduction: runs of equal record index are contiguous; sums end in the run-head lane
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int jo = __shfl_down_sync(0xffffffffu, j, off);
+        const bool same = (lane + off < 32) && (jo == j) && (j >= 0);
+        if (!__any_sync(0xffffffffu, same)) break;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const float vo = __shfl_down_sync(0xffffffffu, v[k], off);
+          if (same) v[k] += vo;
+        }
+      }
+      const int jprev = __shfl_up_sync(0xffffffffu, j, 1);
+      if (j >= 0 && (lane == 0 || jprev != j)) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) part[j][k] += v[k];
+      }
+      __syncwarp();
+      qhead = (qhead + n) & (QCAP - 1);
+      qcount -= n;
+    };
+
+    if (base < wmax) {   // some pixel of this warp reaches into the chunk
+      const int lim = min(cnt, wmax - base);
+      for (int g0i = 0; g0i < lim; g0i += 32) {
+        const int r = g0i + lane;
+        bool hit = false;
+        if (r < lim) hit = box_hits(bb[r], wx0, wx1, wy0, wy1);
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int j = g0i + __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 a = rec[3 * j], b = rec[3 * j + 1];
+          float dx, dy, G, alpha;
+          const bool contrib = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && (base + j < ncontrib);
+          const unsigned cb = __ballot_sync(0xffffffffu, contrib);
+          if (cb == 0u) continue;
+          if (contrib) {
+            const float2 cc = *reinterpret_cast<const float2*>(rec + 3 * j + 2);
+            const float qv = (b.z * g0 + b.w * g1) + (cc.x * g2 + cc.y * gd);
+            P = P + qv * (alpha * T);
+            const int pos = (qhead + qcount + __popc(cb & lt_mask)) & (QCAP - 1);
+            q[pos] = make_uint4((unsigned)j | ((unsigned)lane << 16), __float_as_uint(G), __float_as_uint(T),
+                                __float_as_uint(P));
+            T = T * (1.0f - alpha);
+          }
+          qcount += __popc(cb);
+          if (qcount >= 32) {
+            __syncwarp();
+            dense(32);
+          }
+        }
+      }
+      // the chunk's records leave shared memory after this chunk: drain the queue
+      __syncwarp();
+      if (qcount > 0) dense(qcount);
+    }
+    __syncthreads();
+    // cross-warp reduction in fixed warp order, one plain store per (record, component)
+    for (int i = tid; i < cnt * 10; i += TILE_THREADS) {
+      const int j = i / 10, k = i - j * 10;
+      float sum = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += S.part[w][j][k];
+      const int slot = __float_as_int(reinterpret_cast<const float*>(rec + 3 * j + 2)[2]);
+      dup_grad[(size_t)slot * 12 + k] = sum;
+    }
+    __syncthreads();
+  }
+}
+
 cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                   const SpfRasterGradOut& gout, const SpfRasterGradIn& gin, cudaStream_t s) {
   const int grid = d.B * d.T;
-  if (d.flags & SPF_FLAG_NO_TMA)
-    blend_backward_kernel<false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
-  else
-    blend_backward_kernel<true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+  if (d.flags & SPF_FLAG_BWD_V1) {
+    if (d.flags & SPF_FLAG_NO_TMA)
+      blend_backward_v1_kernel<false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+    else
+      blend_backward_v1_kernel<true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+    return cudaGetLastError();
+  }
+  const size_t smem = sizeof(BwdSmem);
+  cudaError_t e;
+  if (d.flags & SPF_FLAG_NO_TMA) {
+    e = cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    blend_backward_kernel<false><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad);
+  } else {
+    e = cudaFuncSetAttribute(blend_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    blend_backward_kernel<true><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad);
+  }
   return cudaGetLastError();
 }
 

@@ -80,9 +80,9 @@ int check_state(const SpfRasterState* st) {
   if (!st) return fail(SPF_ERR_BAD_ARG, "state is NULL");
   if (!st->xy || !st->depth || !st->conic_opacity || !st->rgb || !st->radii || !st->tiles_touched ||
       !st->dup_offset || !st->control || !st->bucket || !st->slab || !st->cullbox || !st->tile_ranges || !st->final_T ||
-      !st->n_contrib)
+      !st->n_contrib || !st->accum)
     return fail(SPF_ERR_BAD_ARG, "every SpfRasterState buffer must be provided");
-  if ((reinterpret_cast<uintptr_t>(st->slab) & 15) || (reinterpret_cast<uintptr_t>(st->cullbox) & 15) || (reinterpret_cast<uintptr_t>(st->conic_opacity) & 15) ||
+  if ((reinterpret_cast<uintptr_t>(st->slab) & 15) || (reinterpret_cast<uintptr_t>(st->accum) & 15) || (reinterpret_cast<uintptr_t>(st->cullbox) & 15) || (reinterpret_cast<uintptr_t>(st->conic_opacity) & 15) ||
       (reinterpret_cast<uintptr_t>(st->xy) & 7) || (reinterpret_cast<uintptr_t>(st->bucket) & 7))
     return fail(SPF_ERR_BAD_ARG, "state buffers are not sufficiently aligned (slab/conic 16 B, xy/bucket 8 B)");
   return 0;

@@ -67,6 +67,7 @@ class RasterSettings:
     want_alpha: bool = False
     want_means2d_grad: bool = False
     no_tma: bool = False
+    bwd_v1: bool = False                # debugging: first-generation blend backward
 
     def flags(self) -> int:
         f = 0
@@ -80,6 +81,8 @@ class RasterSettings:
             f |= L.SPF_FLAG_QUAT_XYZW
         if self.no_tma or os.environ.get("SPF_NO_TMA") == "1":
             f |= L.SPF_FLAG_NO_TMA
+        if self.bwd_v1 or os.environ.get("SPF_BWD_V1") == "1":
+            f |= L.SPF_FLAG_BWD_V1
         return f
 
 
@@ -125,7 +128,7 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
         rgb=torch.empty(B, P, 3, **f32), radii=torch.empty(B, P, **i32), tiles_touched=torch.empty(B, P, **i32),
         dup_offset=torch.empty(B, P, **i32), control=torch.empty(n_ctrl, **i32),
         tile_ranges=torch.empty(B * T, 2, **i32), final_T=torch.empty(B, H, W, **f32),
-        n_contrib=torch.empty(B, H, W, **i32))
+        n_contrib=torch.empty(B, H, W, **i32), accum=torch.empty(B, H, W, 4, **f32))
     color = torch.empty(B, 3, H, W, **f32)
     depth = torch.empty(B, 1, H, W, **f32)
     alpha = torch.empty(B, 1, H, W, **f32) if s.want_alpha else None
@@ -141,7 +144,7 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
         t["cullbox"] = torch.empty(cap, 4, **f32)
         cstate = L.SpfRasterState(*[_ptr(t[k]) for k in ("xy", "depth", "conic_opacity", "rgb", "radii",
                                                         "tiles_touched", "dup_offset", "control", "bucket",
-                                                        "slab", "cullbox", "tile_ranges", "final_T", "n_contrib")],
+                                                        "slab", "cullbox", "tile_ranges", "final_T", "n_contrib", "accum")],
                                   _ptr(host_t))
         cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
         L.check(lib.spf_raster_forward(C.byref(desc), C.byref(cin), C.byref(cstate), C.byref(cout), stream),
