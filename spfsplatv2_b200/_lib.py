@@ -24,7 +24,7 @@ class SpfRasterDesc(C.Structure):
     _fields_ = [("n_scenes", C.c_int32), ("views_per_scene", C.c_int32), ("n_gaussians", C.c_int32),
                 ("image_height", C.c_int32), ("image_width", C.c_int32), ("sh_degree", C.c_int32),
                 ("flags", C.c_uint32), ("scale_modifier", C.c_float), ("dup_capacity", C.c_int64),
-                ("ticket", C.c_int32)]
+                ("ticket", C.c_int32), ("pair_capacity", C.c_int32)]
 
 
 class SpfRasterIn(C.Structure):
@@ -36,7 +36,7 @@ class SpfRasterIn(C.Structure):
 class SpfRasterState(C.Structure):
     _fields_ = [("xy", _fp), ("depth", _fp), ("conic_opacity", _fp), ("rgb", _fp), ("radii", _fp),
                 ("tiles_touched", _fp), ("dup_offset", _fp), ("control", _fp), ("bucket", _fp), ("slab", _fp),
-                ("cullbox", _fp), ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp), ("accum", _fp), ("host_counters", _fp)]
+                ("cullbox", _fp), ("tile_ranges", _fp), ("final_T", _fp), ("n_contrib", _fp), ("accum", _fp), ("pair_log", _fp), ("pair_count", _fp), ("host_counters", _fp)]
 
 
 class SpfRasterOut(C.Structure):

@@ -66,12 +66,21 @@ __device__ __forceinline__ bool box_hits(const float4& bb, float x0, float x1, f
   return (bb.x <= x1) && (bb.y >= x0) && (bb.z <= y1) && (bb.w >= y0);
 }
 
-template <bool TMA>
+// Pair log (LOG = true, enabled when a backward pass will follow): every warp appends one 32-byte record per
+// CONTRIBUTING (pixel, Gaussian) pair, in hit order (pairs of one Gaussian adjacent, in lane order):
+//   word0 = record index in the tile list | lane << 25;  G;  T_before;  the blended sums (rgb, depth) AFTER this pair.
+// With these the backward needs no per-pixel sequential pass at all (see blend_backward_log_kernel).  A warp's
+// segment holds `pair_capacity` records; a warp that needs more stops writing and reports -1 (its tile is then
+// handled by the recomputing v2 backward).  The largest per-warp count goes to control[2] for the host's sizing.
+constexpr unsigned PAIR_J_MASK = (1u << 25) - 1u;
+
+template <bool TMA, bool LOG>
 __global__ void __launch_bounds__(TILE_THREADS)
 blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterOut out) {
   __shared__ __align__(128) float4 buf[2][CH_F * 3];
   __shared__ __align__(128) float4 box[2][CH_F];
   __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int blk_pairs;
   const int tid = threadIdx.x, lane = tid & 31;
   const int t = blockIdx.x;
   const int view = t / d.T, tile = t - view * d.T;
@@ -83,13 +92,21 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   const bool inside = (px < d.W) && (py < d.H);
   const float pxf = (float)px, pyf = (float)py;
   const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
-  if (TMA) {
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  if (TMA || LOG) {
+    if (tid == 0) {
+      if (TMA) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+      blk_pairs = 0;
+    }
     __syncthreads();
   }
   const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
   const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
   const int nchunks = (L + CH_F - 1) / CH_F;
+  const int Cw = d.pair_cap;
+  uint4* plog = LOG ? reinterpret_cast<uint4*>(st.pair_log) + ((size_t)t * 8 + (tid >> 5)) * (size_t)Cw * 2 : nullptr;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned lane_bits = (unsigned)lane << 25;
+  int room = Cw;   // pair-log records this warp may still write
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
   int last = 0;
@@ -125,6 +142,7 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
           bool ok = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && !done;
           const float test_T = T * (1.0f - alpha);
           if (ok && test_T < T_STOP) { done = true; ok = false; }
+          const float Tb = T;
           if (ok) {
             const float4 cc = rec[3 * j + 2];
             const float w = alpha * T;
@@ -132,12 +150,34 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
             T = test_T;
             last = base + j + 1;
           }
+          if (LOG) {
+            const unsigned cb = __ballot_sync(0xffffffffu, ok);
+            if (cb) {
+              const int n = __popc(cb);
+              room -= n;             // keeps counting past the capacity: reports the size that would have been needed
+              if (ok && room >= 0) {
+                uint4* dst = plog + 2 * __popc(cb & lt_mask);
+                dst[0] = make_uint4((unsigned)(base + j) | lane_bits, __float_as_uint(G), __float_as_uint(Tb), __float_as_uint(C0));
+                dst[1] = make_uint4(__float_as_uint(C1), __float_as_uint(C2), __float_as_uint(D), 0u);
+              }
+              plog += 2 * n;
+            }
+          }
         }
       }
     }
     if (__syncthreads_and(done)) break;
   }
   if (TMA && pending >= 0 && tid == 0) mbar_wait(&bar[pending & 1], (uint32_t)((pending >> 1) & 1));
+  if (LOG) {
+    if (lane == 0) {
+      const int npairs = Cw - room;
+      st.pair_count[(size_t)t * 8 + (tid >> 5)] = (room >= 0 && L <= (int)PAIR_J_MASK) ? npairs : -1;
+      atomicMax(&blk_pairs, npairs);
+    }
+    __syncthreads();
+    if (tid == 0 && blk_pairs > 0) atomicMax(st.control + 2, blk_pairs);
+  }
 
   if (inside) {
     const float* bg = bg_all + view * 3;
@@ -160,10 +200,14 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
 cudaError_t launch_blend_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                  const SpfRasterOut& out, cudaStream_t s) {
   const int grid = d.B * d.T;
-  if (d.flags & SPF_FLAG_NO_TMA)
-    blend_forward_kernel<false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
-  else
-    blend_forward_kernel<true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+  const bool log = st.pair_log != nullptr && st.pair_count != nullptr && d.pair_cap > 0;
+  if (d.flags & SPF_FLAG_NO_TMA) {
+    if (log) blend_forward_kernel<false, true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+    else blend_forward_kernel<false, false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+  } else {
+    if (log) blend_forward_kernel<true, true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+    else blend_forward_kernel<true, false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+  }
   return cudaGetLastError();
 }
 
@@ -388,7 +432,7 @@ struct BwdSmem {
 template <bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS, 3)
 blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
-                      float* __restrict__ dup_grad) {
+                      float* __restrict__ dup_grad, int use_log) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
 
@@ -398,6 +442,12 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
   const int L = e - s;
   if (L == 0) return;
+  if (use_log) {   // tiles whose 8 warp logs are complete were handled by blend_backward_log_kernel
+    bool neg = false;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) neg |= st.pair_count[(size_t)t * 8 + w] < 0;
+    if (!neg) return;
+  }
   int bx, by;
   warp_block_of_thread(tid, tile, d.gx, bx, by);
   const int px = bx + (lane & 7), py = by + (lane >> 3);
@@ -576,6 +626,213 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Blend backward, v3: consumes the forward's pair log -- no alpha tests, no per-pixel sequential state.
+//
+// For a logged pair i of pixel p:  dL/dalpha_i = T_i q_i - (Qtot_p - g_p . S_i) / (1 - alpha_i), with S_i the blended
+// sums after the pair (logged), g_p = (dL/dC, dL/dD) and Qtot_p = g_p . S_final + T_final (bg . dL/dC - dL/dA).
+// Every pair is independent: warp w walks the log of forward-warp w 32 pairs at a time, ONE PAIR PER LANE (whole
+// runs only: a batch is cut at the last run boundary, so a Gaussian's pairs of this warp are always reduced in
+// one segmented shuffle reduction).  A Gaussian whose alpha box overlaps a single 8x4 warp region (the common case
+// with SPFSplatV2's ~2 px splats) is final after that reduction and its 10 sums are stored straight to its
+// duplicate slot; one that overlaps several regions parks its per-warp sums in shared-memory exchange slots that
+// are added in fixed region order after ONE block barrier.  No atomics on floats, fixed order: bit-reproducible.
+// Tiles with an incomplete log, a list longer than LOG_LCAP or too many multi-region records are left to the
+// recomputing kernel above (flagged through pair_count).
+constexpr int LOG_LCAP = 1024;     // longest tile list handled here
+constexpr int LOG_ESLOTS = 512;    // exchange slots (one per (multi-region record, overlapped region))
+
+struct LogSmem {
+  float4 pg[TILE_THREADS];
+  float pq[TILE_THREADS];
+  uint32_t info[LOG_LCAP];               // region mask (8 bits) | first exchange slot << 8
+  float exch[LOG_ESLOTS][10];
+  uint32_t wrote[LOG_LCAP / 32];
+  int warp_tot[8];
+  int base;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS)
+blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
+                          float* __restrict__ dup_grad) {
+  __shared__ __align__(16) LogSmem S;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t = blockIdx.x;
+  const int view = t / d.T, tile = t - view * d.T;
+  const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
+  const int L = e - s;
+  if (L == 0) return;
+  const int count = st.pair_count[(size_t)t * 8 + wid];
+  if (__syncthreads_or(count < 0)) return;            // incomplete log: the recomputing kernel takes this tile
+  if (L > LOG_LCAP) {
+    if (tid == 0) st.pair_count[(size_t)t * 8] = -1;
+    return;
+  }
+  int bx, by;
+  warp_block_of_thread(tid, tile, d.gx, bx, by);
+  const int px = bx + (lane & 7), py = by + (lane >> 3);
+  const bool inside = (px < d.W) && (py < d.H);
+  const size_t hw = (size_t)d.H * d.W;
+  const size_t pix = (size_t)py * d.W + px;
+  const int tx0 = (tile % d.gx) * TILE, ty0 = (tile / d.gx) * TILE;
+  const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
+  const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
+
+  // per-pixel upstream gradients and Qtot
+  {
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, gd = 0.f, qtot = 0.f;
+    if (inside) {
+      float ga = 0.f;
+      if (go.dL_dcolor) {
+        const float* gc = go.dL_dcolor + (size_t)view * 3 * hw;
+        g0 = gc[pix]; g1 = gc[hw + pix]; g2 = gc[2 * hw + pix];
+      }
+      if (go.dL_ddepth) gd = go.dL_ddepth[(size_t)view * hw + pix];
+      if (go.dL_dalpha) ga = go.dL_dalpha[(size_t)view * hw + pix];
+      const float4 acc = reinterpret_cast<const float4*>(st.accum)[(size_t)view * hw + pix];
+      const float* bg = bg_all + view * 3;
+      const float bgdot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2 - ga;
+      qtot = (acc.x * g0 + acc.y * g1) + (acc.z * g2 + acc.w * gd) + st.final_T[(size_t)view * hw + pix] * bgdot;
+    }
+    S.pg[tid] = make_float4(g0, g1, g2, gd);
+    S.pq[tid] = qtot;
+  }
+  // which 8x4 warp regions does each record's alpha box overlap (the same box_hits test the forward used), and
+  // exchange-slot assignment for records overlapping more than one
+  if (tid == 0) S.base = 0;
+  for (int i = tid; i < LOG_LCAP / 32; i += TILE_THREADS) S.wrote[i] = 0u;
+  {
+    float4* z = reinterpret_cast<float4*>(&S.exch[0][0]);
+    for (int i = tid; i < LOG_ESLOTS * 10 / 4; i += TILE_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  for (int r0 = 0; r0 < L; r0 += TILE_THREADS) {
+    const int r = r0 + tid;
+    unsigned mask = 0u;
+    if (r < L) {
+      const float4 bb = __ldg(cull + r);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float x0 = (float)(tx0 + (w & 1) * 8), y0 = (float)(ty0 + (w >> 1) * 4);
+        if (box_hits(bb, x0, x0 + 7.0f, y0, y0 + 3.0f)) mask |= 1u << w;
+      }
+    }
+    const int nreg = __popc(mask);
+    const int need = nreg > 1 ? nreg : 0;
+    const int inc = warp_incl_scan_i(need, lane);
+    if (lane == 31) S.warp_tot[wid] = inc;
+    __syncthreads();
+    int off = S.base;
+    for (int w = 0; w < wid; ++w) off += S.warp_tot[w];
+    if (r < L) S.info[r] = mask | ((unsigned)(off + inc - need) << 8);
+    __syncthreads();
+    if (tid == TILE_THREADS - 1) S.base = off + inc;
+  }
+  __syncthreads();
+  if (S.base > LOG_ESLOTS) {
+    if (tid == 0) st.pair_count[(size_t)t * 8] = -1;
+    return;
+  }
+
+  const uint4* lp = reinterpret_cast<const uint4*>(st.pair_log) + ((size_t)t * 8 + wid) * (size_t)d.pair_cap * 2;
+  const float4* pgw = S.pg + wid * 32;
+  const float* pqw = S.pq + wid * 32;
+  int p0 = 0;
+  while (p0 < count) {
+    const int idx = p0 + lane;
+    const bool valid = idx < count;
+    uint4 e0 = make_uint4(0u, 0u, 0u, 0u), e1 = e0;
+    if (valid) { e0 = lp[2 * (size_t)idx]; e1 = lp[2 * (size_t)idx + 1]; }
+    // run boundaries: a run = the pairs of one record (adjacent, <= 32).  The batch starts at a run head; it is cut
+    // after the last boundary so that every run is reduced whole (no boundary at all = one full 32-pair run).
+    const int jraw = valid ? (int)(e0.x & PAIR_J_MASK) : -2;
+    const int jnext = __shfl_down_sync(0xffffffffu, jraw, 1);
+    const bool bnd = valid && ((lane == 31) ? (idx + 1 == count) : (jnext != jraw));
+    const unsigned bm = __ballot_sync(0xffffffffu, bnd);
+    const int ncomp = bm ? 32 - __clz(bm) : 32;      // pairs of complete runs in this batch
+    const bool act = lane < ncomp && valid;
+    int j = -1;
+    float v[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) v[k] = 0.0f;
+    int slot = 0;
+    if (act) {
+      j = (int)(e0.x & PAIR_J_MASK);
+      const int pl = (int)((e0.x >> 25) & 31u);
+      const float G = __uint_as_float(e0.y), Tb = __uint_as_float(e0.z);
+      const float4 a = __ldg(slab + 3 * j), b = __ldg(slab + 3 * j + 1), cc = __ldg(slab + 3 * j + 2);
+      slot = __float_as_int(cc.z);
+      const float4 g = pgw[pl];
+      const float dx = a.x - (float)(bx + (pl & 7)), dy = a.y - (float)(by + (pl >> 3));
+      const float alpha = fminf(ALPHA_MAX, b.y * G);
+      const float qv = (b.z * g.x + b.w * g.y) + (cc.x * g.z + cc.y * g.w);
+      const float sg = (__uint_as_float(e0.w) * g.x + __uint_as_float(e1.x) * g.y) +
+                       (__uint_as_float(e1.y) * g.z + __uint_as_float(e1.z) * g.w);
+      const float dL_dalpha = Tb * qv - __fdividef(pqw[pl] - sg, 1.0f - alpha);
+      const float dL_dG = b.y * dL_dalpha;
+      const float gdx = G * dx, gdy = G * dy;
+      v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
+      v[1] = dL_dG * (-gdy * b.x - gdx * a.w);
+      v[2] = -0.5f * gdx * dx * dL_dG;
+      v[3] = -gdx * dy * dL_dG;
+      v[4] = -0.5f * gdy * dy * dL_dG;
+      v[5] = G * dL_dalpha;
+      const float w = alpha * Tb;
+      v[6] = w * g.x; v[7] = w * g.y; v[8] = w * g.z; v[9] = w * g.w;
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int jo = __shfl_down_sync(0xffffffffu, j, off);
+      const bool same = (lane + off < 32) && (jo == j) && (j >= 0);
+      if (!__any_sync(0xffffffffu, same)) break;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const float vo = __shfl_down_sync(0xffffffffu, v[k], off);
+        if (same) v[k] += vo;
+      }
+    }
+    const int jprev = __shfl_up_sync(0xffffffffu, j, 1);
+    if (act && (lane == 0 || jprev != j)) {          // run head: holds this warp's sums for record j
+      const unsigned info = S.info[j];
+      const unsigned mask = info & 0xffu;
+      if (__popc(mask) <= 1) {
+        float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+        atomicOr(&S.wrote[j >> 5], 1u << (j & 31));
+      } else {
+        float* ex = S.exch[(info >> 8) + __popc(mask & ((1u << wid) - 1u))];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) ex[k] = v[k];
+      }
+    }
+    p0 += ncomp;
+  }
+  __syncthreads();
+  // multi-region records: add the regions' sums in region order; untouched single-region records: zeros
+  for (int r = tid; r < L; r += TILE_THREADS) {
+    const unsigned info = S.info[r];
+    const int nreg = __popc(info & 0xffu);
+    float v[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) v[k] = 0.0f;
+    if (nreg > 1) {
+      const float* ex = S.exch[info >> 8];
+      for (int o = 0; o < nreg; ++o)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] += ex[o * 10 + k];
+    } else if ((S.wrote[r >> 5] >> (r & 31)) & 1u) {
+      continue;
+    }
+    const int slot = __float_as_int(__ldg(reinterpret_cast<const float*>(slab + 3 * r + 2) + 2));
+    float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+  }
+}
+
 cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                   const SpfRasterGradOut& gout, const SpfRasterGradIn& gin, cudaStream_t s) {
   const int grid = d.B * d.T;
@@ -586,16 +843,22 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
       blend_backward_v1_kernel<true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
     return cudaGetLastError();
   }
+  const bool use_log = st.pair_log != nullptr && st.pair_count != nullptr && d.pair_cap > 0;
+  if (use_log) {
+    blend_backward_log_kernel<<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return e0;
+  }
   const size_t smem = sizeof(BwdSmem);
   cudaError_t e;
   if (d.flags & SPF_FLAG_NO_TMA) {
     e = cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    blend_backward_kernel<false><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad);
+    blend_backward_kernel<false><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
   } else {
     e = cudaFuncSetAttribute(blend_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    blend_backward_kernel<true><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad);
+    blend_backward_kernel<true><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
   }
   return cudaGetLastError();
 }

@@ -39,6 +39,7 @@ bool make_dims(const SpfRasterDesc* desc, int sh_coeffs, bool use_sh, spf::Dims&
   d.mod = desc->scale_modifier;
   d.cap = desc->dup_capacity;
   d.ticket = desc->ticket;
+  d.pair_cap = desc->pair_capacity;
   (void)sh_coeffs; (void)use_sh;
   return true;
 }

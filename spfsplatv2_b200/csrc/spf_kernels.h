@@ -35,6 +35,7 @@ struct Dims {
   float mod;
   int64_t cap;
   int ticket;
+  int pair_cap;   // pair-log records per warp (0 = no log)
 };
 
 cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,

@@ -28,6 +28,12 @@ _capacity_hint: dict = {}
 GROWTH = 1.25
 _host_counters: dict = {}     # device index -> (pinned int32[2] tensor, numpy view)
 _ticket = [0]
+# Pair-log sizing (records per warp): per-shape high-water mark of control[2], fed back asynchronously after each
+# backward (pinned copy + event, polled -- never waited on -- by the next forward of that shape).
+_pair_cap_hint: dict = {}
+_pair_stat: dict = {}         # key -> (pinned int32[1], event)
+PAIR_CAP_DEFAULT = 512
+PAIR_LOG_BUDGET = 4 << 30     # bytes; above this the capacity is clipped and the densest tiles fall back to recomputation
 
 
 def _counters(dev):
@@ -68,6 +74,7 @@ class RasterSettings:
     want_means2d_grad: bool = False
     no_tma: bool = False
     bwd_v1: bool = False                # debugging: first-generation blend backward
+    pair_log: bool = True               # forward logs contributing pairs for the backward (when grads are needed)
 
     def flags(self) -> int:
         f = 0
@@ -88,11 +95,26 @@ class RasterSettings:
 
 class _State:
     """Forward intermediates kept for backward / inspection (plain tensors, not autograd-tracked)."""
-    __slots__ = ("desc", "cin", "cstate", "keep", "n_dups", "capacity", "tensors")
+    __slots__ = ("desc", "cin", "cstate", "keep", "n_dups", "capacity", "tensors", "key")
+
+
+def _pair_capacity(key, n_warps: int) -> int:
+    """Records per warp for the next forward of this shape.  The capacity only ever GROWS, and only when the previous
+    backward of this shape reported an overflow; the feedback is applied at a deterministic point (here, waiting for
+    the tiny copy if it has not landed yet -- it was issued a whole backward ago), so a run is reproducible."""
+    st = _pair_stat.pop(key, None)
+    cap = int(_pair_cap_hint.get(key, PAIR_CAP_DEFAULT))
+    if st is not None:
+        st[1].synchronize()
+        need = int(st[0][0])
+        if need > cap:
+            cap = ((int(need * 1.25) + 63) // 64) * 64
+            _pair_cap_hint[key] = cap
+    return max(64, min(cap, (PAIR_LOG_BUDGET // (32 * max(n_warps, 1))) // 64 * 64))
 
 
 def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg,
-                  pre_scale):
+                  pre_scale, pair_log: bool = False):
     lib = L.lib()
     dev = means.device
     if dev.type != "cuda":
@@ -116,7 +138,8 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     key = (dev.index, S, v, P, H, W)
     cap = max(int(_capacity_hint.get(key, 2 * B * P)), 1024)
 
-    desc = L.SpfRasterDesc(S, v, P, H, W, s.sh_degree, s.flags(), float(s.scale_modifier), cap)
+    pair_cap = _pair_capacity(key, B * T * 8) if (pair_log and s.pair_log) else 0
+    desc = L.SpfRasterDesc(S, v, P, H, W, s.sh_degree, s.flags(), float(s.scale_modifier), cap, 0, pair_cap)
     n_ctrl = lib.spf_raster_control_ints(C.byref(desc))
     if n_ctrl < 0:
         L.check(-1, "spf_raster_control_ints")
@@ -129,6 +152,9 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
         dup_offset=torch.empty(B, P, **i32), control=torch.empty(n_ctrl, **i32),
         tile_ranges=torch.empty(B * T, 2, **i32), final_T=torch.empty(B, H, W, **f32),
         n_contrib=torch.empty(B, H, W, **i32), accum=torch.empty(B, H, W, 4, **f32))
+    if pair_cap > 0:
+        t["pair_log"] = torch.empty(B * T * 8, pair_cap, 8, **f32)
+        t["pair_count"] = torch.empty(B * T * 8, **i32)
     color = torch.empty(B, 3, H, W, **f32)
     depth = torch.empty(B, 1, H, W, **f32)
     alpha = torch.empty(B, 1, H, W, **f32) if s.want_alpha else None
@@ -145,7 +171,7 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
         cstate = L.SpfRasterState(*[_ptr(t[k]) for k in ("xy", "depth", "conic_opacity", "rgb", "radii",
                                                         "tiles_touched", "dup_offset", "control", "bucket",
                                                         "slab", "cullbox", "tile_ranges", "final_T", "n_contrib", "accum")],
-                                  _ptr(host_t))
+                                  _ptr(t.get("pair_log")), _ptr(t.get("pair_count")), _ptr(host_t))
         cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
         L.check(lib.spf_raster_forward(C.byref(desc), C.byref(cin), C.byref(cstate), C.byref(cout), stream),
                 "spf_raster_forward")
@@ -166,6 +192,7 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
 
     st = _State()
     st.desc, st.cin, st.cstate, st.n_dups, st.capacity, st.tensors = desc, cin, cstate, n_dups, cap, t
+    st.key = key
     st.keep = (means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale)
     return color, depth, alpha, t["radii"], st
 
@@ -176,7 +203,7 @@ class _Rasterize(torch.autograd.Function):
                 bg, pre_scale, means2d):
         args = [None if a is None else _f32c(a.detach()) for a in
                 (means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale)]
-        color, depth, alpha, radii, st = _forward_impl(settings, *args)
+        color, depth, alpha, radii, st = _forward_impl(settings, *args, pair_log=any(ctx.needs_input_grad))
         ctx.settings = settings
         ctx.st = st
         ctx.shapes = (means.shape, scales.shape, rots.shape, opac.shape,
@@ -217,6 +244,13 @@ class _Rasterize(torch.autograd.Function):
                                 _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
         L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
                                         C.byref(gin), _stream(dev)), "spf_raster_backward")
+        if st.desc.pair_capacity > 0 and st.key not in _pair_stat:
+            # feed the largest per-warp pair count back to the sizing of the next forward (no wait)
+            pin = torch.empty(1, dtype=torch.int32).pin_memory()
+            pin.copy_(st.tensors["control"][2:3], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            _pair_stat[st.key] = (pin, ev)
         sh = ctx.shapes
         return (None, d_means.view(sh[0]), d_scales.view(sh[1]), d_rots.view(sh[2]), d_opac.view(sh[3]),
                 None if d_shs is None else d_shs.view(sh[4]), None if d_cols is None else d_cols.view(sh[5]),
@@ -238,11 +272,11 @@ def rasterize_batched(settings: RasterSettings, means: Tensor, scales: Tensor, r
 
 
 def forward_with_state(settings: RasterSettings, means, scales, rotations, opacities, shs, colors, viewmatrix,
-                       projmatrix, tanfov, bg, pre_scale=None):
+                       projmatrix, tanfov, bg, pre_scale=None, pair_log: bool = False):
     """No-autograd forward that also returns the intermediate state (for parity tests / profiling)."""
     args = [None if a is None else _f32c(a.detach()) for a in
             (means, scales, rotations, opacities, shs, colors, viewmatrix, projmatrix, tanfov, bg, pre_scale)]
-    return _forward_impl(settings, *args)
+    return _forward_impl(settings, *args, pair_log=pair_log)
 
 
 def unpack_sorted(st: _State):
@@ -267,7 +301,7 @@ def profile_stages(settings: RasterSettings, means, scales, rotations, opacities
     stream.  Used by bench.py for the roofline of the dominant kernel."""
     lib = L.lib()
     color, depth, alpha, radii, st = forward_with_state(settings, means, scales, rotations, opacities, shs, colors,
-                                                        viewmatrix, projmatrix, tanfov, bg, pre_scale)
+                                                        viewmatrix, projmatrix, tanfov, bg, pre_scale, pair_log=True)
     means_c, scales_c, rots_c, opac_c, shs_c, cols_c = st.keep[:6]
     dev = means_c.device
     S, P = means_c.shape[0], means_c.shape[1]

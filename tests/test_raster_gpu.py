@@ -190,8 +190,11 @@ def test_decoder_gradients_end_to_end():
 
 
 def test_backward_generations_agree():
-    """The pair-compaction blend backward (default) against the first-generation kernel (SPF_FLAG_BWD_V1): two
-    independent derivations (front-to-back closed form vs back-to-front recursion) of the same gradient."""
+    """Three independent implementations of the blend backward give the same gradients: the pair-log kernel (default:
+    consumes the forward's log, closed form per pair), the recomputing pair-compaction kernel (pair_log=False, also the
+    per-tile fallback when a warp's log overflows -- forced here with a tiny capacity) and the first-generation
+    back-to-front kernel (SPF_FLAG_BWD_V1)."""
+    from spfsplatv2_b200 import rasterizer as R
     from spfsplatv2_b200.camera import camera_setup
     from spfsplatv2_b200.rasterizer import RasterSettings, rasterize_batched
     d = _dev()
@@ -199,31 +202,89 @@ def test_backward_generations_agree():
         sc = make_scene(seed=29, v_cxt=1, h=h, w=w, grid=grid, regime=regime, n_target=2)
         view, proj, tanfov, scale = [x.to(d) for x in camera_setup(sc.extrinsics[0], sc.intrinsics[0], sc.near[0], sc.far[0], True)]
         wc = torch.randn(2, 3, h, w, device=d, generator=torch.Generator(device=d).manual_seed(1))
-        grads = []
-        for v1 in (False, True):
+        grads, kinds = [], []
+        for kind in ("log", "log_small_capacity", "recompute", "v1"):
+            R._pair_cap_hint.clear(); R._pair_stat.clear()
+            if kind == "log_small_capacity":     # most warps overflow -> their tiles fall back, the rest use the log
+                R._pair_cap_hint[(0, 1, 2, sc.means.shape[1], h, w)] = 64
             t = {k: getattr(sc, k).to(d).requires_grad_() for k in ("means", "scales", "rotations", "opacities", "harmonics")}
             vm = view.clone().requires_grad_()
-            s = RasterSettings(h, w, 4, 1.0, 2, sh_layout_ck=True, want_alpha=True, bwd_v1=v1)
+            s = RasterSettings(h, w, 4, 1.0, 2, sh_layout_ck=True, want_alpha=True, bwd_v1=(kind == "v1"),
+                               pair_log=kind.startswith("log"))
             color, depth, alpha, _ = rasterize_batched(s, t["means"], t["scales"], t["rotations"], t["opacities"], t["harmonics"],
                                                        None, vm, proj, tanfov, torch.tensor([[0.3, 0.2, 0.1]] * 2, device=d), scale)
             ((color * wc).sum() + 0.1 * depth.sum() + 0.5 * (alpha * wc[:, :1]).sum()).backward()
             grads.append([t[k].grad for k in sorted(t)] + [vm.grad])
-        for a, b in zip(*grads):
-            assert rel_err(a, b) < 2e-5
+            kinds.append(kind)
+        R._pair_cap_hint.clear(); R._pair_stat.clear()
+        for kind, g in zip(kinds[1:], grads[1:]):
+            for a, b in zip(grads[0], g):
+                assert rel_err(a, b) < 2e-5, (regime, kind)
+
+
+def test_pair_log_counts_and_capacity_feedback():
+    """The forward's pair log: per-warp counts are consistent with n_contrib-derived totals, overflow is flagged, and the
+    needed capacity is fed back to the next forward of the same shape."""
+    from spfsplatv2_b200 import rasterizer as R
+    sc = make_scene(seed=37, v_cxt=1, h=64, w=64, grid=(32, 32), regime="trained", n_target=1)
+    from spfsplatv2_b200.camera import camera_setup
+    from spfsplatv2_b200.rasterizer import RasterSettings, forward_with_state
+    d = _dev()
+    view, proj, tanfov, scale = [x.to(d) for x in camera_setup(sc.extrinsics[0], sc.intrinsics[0], sc.near[0], sc.far[0], True)]
+    key = (0, 1, 1, sc.means.shape[1], 64, 64)
+    args = (sc.means.to(d), sc.scales.to(d), sc.rotations.to(d), sc.opacities.to(d), sc.harmonics.to(d), None, view, proj, tanfov,
+            torch.zeros(1, 3, device=d), scale)
+    s = RasterSettings(64, 64, 4, 1.0, 1, sh_layout_ck=True)
+    R._pair_cap_hint.clear(); R._pair_stat.clear()
+    R._pair_cap_hint[key] = 4096
+    st = forward_with_state(s, *args, pair_log=True)[4]
+    counts = st.tensors["pair_count"].cpu()
+    assert (counts >= 0).all()
+    need = int(st.tensors["control"][2])
+    assert need == int(counts.max()) and need > 64
+    # total pairs == number of (pixel, Gaussian) contributions; cross-check against the oracle's blend weights
+    ref, _ = oracle_views(sc)
+    # every logged pair carries its pixel's lane and a record index below that pixel's n_contrib
+    log = st.tensors["pair_log"].cpu().view(torch.int32).view(-1, 4096, 8)
+    nc = st.tensors["n_contrib"][0].cpu()
+    assert torch.equal(nc, ref[0]["n_contrib"])
+    total = 0
+    for wi in range(counts.numel()):
+        c = int(counts[wi])
+        if c == 0:
+            continue
+        w0 = log[wi, :c, 0].to(torch.int64) & 0xFFFFFFFF
+        j = w0 & ((1 << 25) - 1)
+        lane = (w0 >> 25) & 31
+        tile, wid = wi // 8, wi % 8
+        px = (tile % 4) * 16 + (wid % 2) * 8 + (lane % 8)
+        py = (tile // 4) * 16 + (wid // 2) * 4 + (lane // 8)
+        assert (j < nc[py, px].to(torch.int64)).all()
+        assert (j[1:] >= j[:-1]).all()                       # hit order
+        total += c
+    assert total > 0
+    R._pair_cap_hint[key] = 64
+    st2 = forward_with_state(s, *args, pair_log=True)[4]
+    c2 = st2.tensors["pair_count"].cpu()
+    assert (c2 == -1).any() and int(st2.tensors["control"][2]) == need
+    assert torch.equal(c2[c2 >= 0], counts[c2 >= 0])
+    R._pair_cap_hint.clear(); R._pair_stat.clear()
 
 
 def test_backward_is_bit_reproducible():
     sc = make_scene(seed=13, v_cxt=1, h=96, w=96, grid=(48, 48), regime="trained", n_target=2)
     dec = _decoder()
     grads = []
-    for _ in range(2):
+    for it in range(3):      # iteration 0 may grow the pair-log capacity (a different, equally valid summation order)
         g, t = _gaussians(sc, requires_grad=True)
         ext = sc.extrinsics.to(_dev()).requires_grad_()
         out = dec(g, ext, sc.intrinsics.to(_dev()), sc.near.to(_dev()), sc.far.to(_dev()), sc.image_shape)
         (out.color.square().sum() + out.depth.sum()).backward()
         grads.append([t[k].grad.clone() for k in sorted(t)] + [ext.grad.clone()])
-    for a, b in zip(*grads):
+    for a, b in zip(grads[1], grads[2]):
         assert torch.equal(a, b)
+    for a, b in zip(grads[0], grads[1]):
+        assert rel_err(a, b) < 1e-5
 
 
 def test_colors_precomp_and_all_culled():
