@@ -430,14 +430,10 @@ struct BwdSmem {
 };
 
 template <bool TMA>
-__global__ void __launch_bounds__(TILE_THREADS, 3)
-blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
-                      float* __restrict__ dup_grad, int use_log) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
-
+__device__ __forceinline__ void blend_backward_tile(const Dims& d, const float* __restrict__ bg_all, const SpfRasterState& st,
+                                                    const SpfRasterGradOut& go, float* __restrict__ dup_grad, int use_log,
+                                                    BwdSmem& S, const int t) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int t = blockIdx.x;
   const int view = t / d.T, tile = t - view * d.T;
   const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
   const int L = e - s;
@@ -626,6 +622,21 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   }
 }
 
+// Grid-stride over (view, tile): with the pair log on, almost every tile is skipped after reading its 8 counters,
+// so the launch is sized to the machine (resident CTAs) instead of one CTA per tile.
+template <bool TMA>
+__global__ void __launch_bounds__(TILE_THREADS, 3)
+blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
+                      float* __restrict__ dup_grad, int use_log) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const int n_tiles = d.B * d.T;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    blend_backward_tile<TMA>(d, bg_all, st, go, dup_grad, use_log, S, t);
+    __syncthreads();     // shared memory (incl. the mbarriers, re-initialised per tile) is reused by the next tile
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Blend backward, v3: consumes the forward's pair log -- no alpha tests, no per-pixel sequential state.
 //
@@ -738,11 +749,11 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
   const float4* pgw = S.pg + wid * 32;
   const float* pqw = S.pq + wid * 32;
   int p0 = 0;
+  uint4 e0 = make_uint4(0u, 0u, 0u, 0u), e1 = e0;
+  if (lane < count) { e0 = lp[2 * (size_t)lane]; e1 = lp[2 * (size_t)lane + 1]; }
   while (p0 < count) {
     const int idx = p0 + lane;
     const bool valid = idx < count;
-    uint4 e0 = make_uint4(0u, 0u, 0u, 0u), e1 = e0;
-    if (valid) { e0 = lp[2 * (size_t)idx]; e1 = lp[2 * (size_t)idx + 1]; }
     // run boundaries: a run = the pairs of one record (adjacent, <= 32).  The batch starts at a run head; it is cut
     // after the last boundary so that every run is reduced whole (no boundary at all = one full 32-pair run).
     const int jraw = valid ? (int)(e0.x & PAIR_J_MASK) : -2;
@@ -751,6 +762,12 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
     const unsigned bm = __ballot_sync(0xffffffffu, bnd);
     const int ncomp = bm ? 32 - __clz(bm) : 32;      // pairs of complete runs in this batch
     const bool act = lane < ncomp && valid;
+    // software pipeline: the next batch's log records are requested before this batch's math
+    uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+    {
+      const int nidx = p0 + ncomp + lane;
+      if (nidx < count) { n0 = lp[2 * (size_t)nidx]; n1 = lp[2 * (size_t)nidx + 1]; }
+    }
     int j = -1;
     float v[10];
 #pragma unroll
@@ -808,6 +825,7 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
       }
     }
     p0 += ncomp;
+    e0 = n0; e1 = n1;
   }
   __syncthreads();
   // multi-region records: add the regions' sums in region order; untouched single-region records: zeros
@@ -850,15 +868,16 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
     if (e0 != cudaSuccess) return e0;
   }
   const size_t smem = sizeof(BwdSmem);
+  const int grid2 = use_log ? min(grid, 148 * 3) : grid;   // fallback-only launch: one wave of resident CTAs
   cudaError_t e;
   if (d.flags & SPF_FLAG_NO_TMA) {
     e = cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    blend_backward_kernel<false><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
+    blend_backward_kernel<false><<<grid2, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
   } else {
     e = cudaFuncSetAttribute(blend_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    blend_backward_kernel<true><<<grid, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
+    blend_backward_kernel<true><<<grid2, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
   }
   return cudaGetLastError();
 }

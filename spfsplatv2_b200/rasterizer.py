@@ -31,7 +31,8 @@ _ticket = [0]
 # Pair-log sizing (records per warp): per-shape high-water mark of control[2], fed back asynchronously after each
 # backward (pinned copy + event, polled -- never waited on -- by the next forward of that shape).
 _pair_cap_hint: dict = {}
-_pair_stat: dict = {}         # key -> (pinned int32[1], event)
+_pair_stat: dict = {}         # key -> [[pinned int32[1], event, age in forwards], ...]
+_pin_pool: list = []          # recycled (pinned int32[1], event) pairs: cudaHostAlloc per step would cost ~100 us
 PAIR_CAP_DEFAULT = 512
 PAIR_LOG_BUDGET = 4 << 30     # bytes; above this the capacity is clipped and the densest tiles fall back to recomputation
 
@@ -98,18 +99,27 @@ class _State:
     __slots__ = ("desc", "cin", "cstate", "keep", "n_dups", "capacity", "tensors", "key")
 
 
+PAIR_FEEDBACK_LAG = 2   # forwards between a backward's report and its use
+
+
 def _pair_capacity(key, n_warps: int) -> int:
-    """Records per warp for the next forward of this shape.  The capacity only ever GROWS, and only when the previous
-    backward of this shape reported an overflow; the feedback is applied at a deterministic point (here, waiting for
-    the tiny copy if it has not landed yet -- it was issued a whole backward ago), so a run is reproducible."""
-    st = _pair_stat.pop(key, None)
+    """Records per warp for the next forward of this shape.  The capacity only ever GROWS, and only when a backward of
+    this shape reported an overflow.  The report (a 4-byte pinned copy issued after that backward) is applied at a
+    deterministic point -- the PAIR_FEEDBACK_LAG-th later forward of the shape -- so runs are reproducible, and by
+    then it has long landed, so the host never stalls the stream it is feeding."""
     cap = int(_pair_cap_hint.get(key, PAIR_CAP_DEFAULT))
-    if st is not None:
-        st[1].synchronize()
-        need = int(st[0][0])
-        if need > cap:
-            cap = ((int(need * 1.25) + 63) // 64) * 64
-            _pair_cap_hint[key] = cap
+    pending = _pair_stat.get(key)
+    if pending:
+        for ent in pending:
+            ent[2] += 1
+        while pending and pending[0][2] >= PAIR_FEEDBACK_LAG:
+            pin, ev, _ = pending.pop(0)
+            ev.synchronize()
+            need = int(pin[0])
+            _pin_pool.append((pin, ev))
+            if need > cap:
+                cap = ((int(need * 1.25) + 63) // 64) * 64
+                _pair_cap_hint[key] = cap
     return max(64, min(cap, (PAIR_LOG_BUDGET // (32 * max(n_warps, 1))) // 64 * 64))
 
 
@@ -244,13 +254,12 @@ class _Rasterize(torch.autograd.Function):
                                 _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
         L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
                                         C.byref(gin), _stream(dev)), "spf_raster_backward")
-        if st.desc.pair_capacity > 0 and st.key not in _pair_stat:
+        if st.desc.pair_capacity > 0 and len(_pair_stat.setdefault(st.key, [])) < 4:
             # feed the largest per-warp pair count back to the sizing of the next forward (no wait)
-            pin = torch.empty(1, dtype=torch.int32).pin_memory()
+            pin, ev = _pin_pool.pop() if _pin_pool else (torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
             pin.copy_(st.tensors["control"][2:3], non_blocking=True)
-            ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
-            _pair_stat[st.key] = (pin, ev)
+            _pair_stat[st.key].append([pin, ev, 0])
         sh = ctx.shapes
         return (None, d_means.view(sh[0]), d_scales.view(sh[1]), d_rots.view(sh[2]), d_opac.view(sh[3]),
                 None if d_shs is None else d_shs.view(sh[4]), None if d_cols is None else d_cols.view(sh[5]),

@@ -275,15 +275,15 @@ def test_backward_is_bit_reproducible():
     sc = make_scene(seed=13, v_cxt=1, h=96, w=96, grid=(48, 48), regime="trained", n_target=2)
     dec = _decoder()
     grads = []
-    for it in range(3):      # iteration 0 may grow the pair-log capacity (a different, equally valid summation order)
+    for it in range(5):      # early iterations may grow the pair-log capacity (a different, equally valid summation order)
         g, t = _gaussians(sc, requires_grad=True)
         ext = sc.extrinsics.to(_dev()).requires_grad_()
         out = dec(g, ext, sc.intrinsics.to(_dev()), sc.near.to(_dev()), sc.far.to(_dev()), sc.image_shape)
         (out.color.square().sum() + out.depth.sum()).backward()
         grads.append([t[k].grad.clone() for k in sorted(t)] + [ext.grad.clone()])
-    for a, b in zip(grads[1], grads[2]):
+    for a, b in zip(grads[3], grads[4]):
         assert torch.equal(a, b)
-    for a, b in zip(grads[0], grads[1]):
+    for a, b in zip(grads[0], grads[4]):
         assert rel_err(a, b) < 1e-5
 
 
