@@ -211,6 +211,7 @@ def run_ours(args):
                             dev_in["harmonics"], None, view, proj, tanfov, torch.zeros(b, 3, device=dev), scale,
                             gcol, None, iters=max(5, args.steps))
         N = st.pop("_n_dups")
+        pair_info = {k[1:]: st.pop(k) for k in list(st) if k.startswith("_")}
         HW = h * w
         algo = {   # SURVEY.md §8(d) per-unit figures x units per launch (B views); see DESIGN.md
             "project_forward": 392.0 * P * b,
@@ -240,6 +241,7 @@ def run_ours(args):
                          "traffic": None, "kernel_ms": round(st[top], 4),
                          "kernel_share_of_step": round(st[top] / kern_ms, 3)},
             "stage_ms": {k: round(v, 4) for k, v in st.items()},
+            "pair_log": pair_info,
             "stage_gbs": {k: round(algo[k] / (st[k] * 1e-3) / 1e9, 1) for k in algo},
             "step_roofline": {"bytes_per_view": round(step_bytes / b), "achieved_gbs": round(step_bytes * world / (ms / args.steps * 1e-3) / 1e9, 1),
                               "frac": round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},

@@ -69,10 +69,12 @@ __device__ __forceinline__ bool box_hits(const float4& bb, float x0, float x1, f
 // Pair log (LOG = true, enabled when a backward pass will follow): every warp appends one 32-byte record per
 // CONTRIBUTING (pixel, Gaussian) pair, in hit order (pairs of one Gaussian adjacent, in lane order):
 //   word0 = record index in the tile list | lane << 25;  G;  T_before;  the blended sums (rgb, depth) AFTER this pair.
+// Runs are padded so that none straddles a 32-record boundary of the log (PAIR_SKIP marker).
 // With these the backward needs no per-pixel sequential pass at all (see blend_backward_log_kernel).  A warp's
 // segment holds `pair_capacity` records; a warp that needs more stops writing and reports -1 (its tile is then
 // handled by the recomputing v2 backward).  The largest per-warp count goes to control[2] for the host's sizing.
 constexpr unsigned PAIR_J_MASK = (1u << 25) - 1u;
+constexpr unsigned PAIR_SKIP = 0xffffffffu;   // word0 of a padding record: the rest of this 32-record block is unused
 
 template <bool TMA, bool LOG>
 __global__ void __launch_bounds__(TILE_THREADS)
@@ -154,6 +156,16 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
             const unsigned cb = __ballot_sync(0xffffffffu, ok);
             if (cb) {
               const int n = __popc(cb);
+              // a run (the pairs of one record) never straddles a 32-record boundary of the log: skip to the next
+              // boundary (one lane leaves a SKIP marker) so that the backward can walk the log in fixed 32-record
+              // batches with every run whole and every batch address known in advance
+              const int pos32 = (Cw - room) & 31;
+              if (pos32 + n > 32) {
+                const int pad = 32 - pos32;
+                if (lane == 0 && room > 0) plog[0].x = PAIR_SKIP;
+                plog += 2 * pad;
+                room -= pad;
+              }
               room -= n;             // keeps counting past the capacity: reports the size that would have been needed
               if (ok && room >= 0) {
                 uint4* dst = plog + 2 * __popc(cb & lt_mask);
@@ -648,25 +660,27 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
 // with SPFSplatV2's ~2 px splats) is final after that reduction and its 10 sums are stored straight to its
 // duplicate slot; one that overlaps several regions parks its per-warp sums in shared-memory exchange slots that
 // are added in fixed region order after ONE block barrier.  No atomics on floats, fixed order: bit-reproducible.
-// Tiles with an incomplete log, a list longer than LOG_LCAP or too many multi-region records are left to the
-// recomputing kernel above (flagged through pair_count).
-constexpr int LOG_LCAP = 1024;     // longest tile list handled here
-constexpr int LOG_ESLOTS = 512;    // exchange slots (one per (multi-region record, overlapped region))
+// Long tile lists are processed in windows of LOG_W records (each warp's log is sorted by record).  Tiles with an
+// incomplete log or too many multi-region records in a window are left to the recomputing kernel above (flagged
+// through pair_count).
+constexpr int LOG_W = 416;         // records per window of the tile list (staged in shared memory)
+constexpr int LOG_ESLOTS = 640;    // exchange slots per window (one per (multi-region record, overlapped region))
 
 struct LogSmem {
+  float4 rec[LOG_W * 3];                 // the window's slab records
   float4 pg[TILE_THREADS];
   float pq[TILE_THREADS];
-  uint32_t info[LOG_LCAP];               // region mask (8 bits) | first exchange slot << 8
+  uint32_t info[LOG_W];                  // region mask (8 bits) | first exchange slot << 8
   float exch[LOG_ESLOTS][10];
-  uint32_t wrote[LOG_LCAP / 32];
-  int warp_tot[8];
+  uint32_t wrote[LOG_W / 32];
   int base;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                           float* __restrict__ dup_grad) {
-  __shared__ __align__(16) LogSmem S;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  LogSmem& S = *reinterpret_cast<LogSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t = blockIdx.x;
   const int view = t / d.T, tile = t - view * d.T;
@@ -675,10 +689,6 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
   if (L == 0) return;
   const int count = st.pair_count[(size_t)t * 8 + wid];
   if (__syncthreads_or(count < 0)) return;            // incomplete log: the recomputing kernel takes this tile
-  if (L > LOG_LCAP) {
-    if (tid == 0) st.pair_count[(size_t)t * 8] = -1;
-    return;
-  }
   int bx, by;
   warp_block_of_thread(tid, tile, d.gx, bx, by);
   const int px = bx + (lane & 7), py = by + (lane >> 3);
@@ -688,6 +698,16 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
   const int tx0 = (tile % d.gx) * TILE, ty0 = (tile / d.gx) * TILE;
   const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
   const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
+  const uint4* lp = reinterpret_cast<const uint4*>(st.pair_log) + ((size_t)t * 8 + wid) * (size_t)d.pair_cap * 2;
+
+  // the log is read in fixed 32-record batches (runs never straddle a batch: the forward pads), so batch addresses do
+  // not depend on data: each batch is prefetched towards the SM three batches ahead and then loaded where it is
+  // used (ptxas does not keep register loads in flight across the loop back-edge, so a register pipeline would
+  // expose the full DRAM latency on every batch)
+  const int nbatch = (count + 31) >> 5;
+  for (int k = 0; k < 3; ++k)
+    if ((k << 5) + lane < count) prefetch_l1(lp + 2 * (size_t)((k << 5) + lane));
+  int bi = 0;
 
   // per-pixel upstream gradients and Qtot
   {
@@ -708,146 +728,143 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
     S.pg[tid] = make_float4(g0, g1, g2, gd);
     S.pq[tid] = qtot;
   }
-  // which 8x4 warp regions does each record's alpha box overlap (the same box_hits test the forward used), and
-  // exchange-slot assignment for records overlapping more than one
-  if (tid == 0) S.base = 0;
-  for (int i = tid; i < LOG_LCAP / 32; i += TILE_THREADS) S.wrote[i] = 0u;
-  {
-    float4* z = reinterpret_cast<float4*>(&S.exch[0][0]);
-    for (int i = tid; i < LOG_ESLOTS * 10 / 4; i += TILE_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();
-  for (int r0 = 0; r0 < L; r0 += TILE_THREADS) {
-    const int r = r0 + tid;
-    unsigned mask = 0u;
-    if (r < L) {
-      const float4 bb = __ldg(cull + r);
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const float x0 = (float)(tx0 + (w & 1) * 8), y0 = (float)(ty0 + (w >> 1) * 4);
-        if (box_hits(bb, x0, x0 + 7.0f, y0, y0 + 3.0f)) mask |= 1u << w;
-      }
-    }
-    const int nreg = __popc(mask);
-    const int need = nreg > 1 ? nreg : 0;
-    const int inc = warp_incl_scan_i(need, lane);
-    if (lane == 31) S.warp_tot[wid] = inc;
-    __syncthreads();
-    int off = S.base;
-    for (int w = 0; w < wid; ++w) off += S.warp_tot[w];
-    if (r < L) S.info[r] = mask | ((unsigned)(off + inc - need) << 8);
-    __syncthreads();
-    if (tid == TILE_THREADS - 1) S.base = off + inc;
-  }
-  __syncthreads();
-  if (S.base > LOG_ESLOTS) {
-    if (tid == 0) st.pair_count[(size_t)t * 8] = -1;
-    return;
-  }
-
-  const uint4* lp = reinterpret_cast<const uint4*>(st.pair_log) + ((size_t)t * 8 + wid) * (size_t)d.pair_cap * 2;
   const float4* pgw = S.pg + wid * 32;
   const float* pqw = S.pq + wid * 32;
-  int p0 = 0;
-  uint4 e0 = make_uint4(0u, 0u, 0u, 0u), e1 = e0;
-  if (lane < count) { e0 = lp[2 * (size_t)lane]; e1 = lp[2 * (size_t)lane + 1]; }
-  while (p0 < count) {
-    const int idx = p0 + lane;
-    const bool valid = idx < count;
-    // run boundaries: a run = the pairs of one record (adjacent, <= 32).  The batch starts at a run head; it is cut
-    // after the last boundary so that every run is reduced whole (no boundary at all = one full 32-pair run).
-    const int jraw = valid ? (int)(e0.x & PAIR_J_MASK) : -2;
-    const int jnext = __shfl_down_sync(0xffffffffu, jraw, 1);
-    const bool bnd = valid && ((lane == 31) ? (idx + 1 == count) : (jnext != jraw));
-    const unsigned bm = __ballot_sync(0xffffffffu, bnd);
-    const int ncomp = bm ? 32 - __clz(bm) : 32;      // pairs of complete runs in this batch
-    const bool act = lane < ncomp && valid;
-    // software pipeline: the next batch's log records are requested before this batch's math
-    uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+
+  for (int w0 = 0; w0 < L; w0 += LOG_W) {
+    const int wn = min(LOG_W, L - w0), wend = w0 + wn;
+    // ---- window prologue: stage the records, region masks (the same box_hits test the forward used), exchange slots
+    if (tid == 0) S.base = 0;
+    for (int i = tid; i < LOG_W / 32; i += TILE_THREADS) S.wrote[i] = 0u;
     {
-      const int nidx = p0 + ncomp + lane;
-      if (nidx < count) { n0 = lp[2 * (size_t)nidx]; n1 = lp[2 * (size_t)nidx + 1]; }
+      float4* z = reinterpret_cast<float4*>(&S.exch[0][0]);
+      for (int i = tid; i < LOG_ESLOTS * 10 / 4; i += TILE_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* src = slab + 3 * (size_t)w0;
+      for (int i = tid; i < wn * 3; i += TILE_THREADS) S.rec[i] = __ldg(src + i);
     }
-    int j = -1;
-    float v[10];
+    __syncthreads();
+    for (int r0 = 0; r0 < wn; r0 += TILE_THREADS) {
+      const int r = r0 + tid;
+      unsigned mask = 0u;
+      if (r < wn) {
+        const float4 bb = __ldg(cull + w0 + r);
 #pragma unroll
-    for (int k = 0; k < 10; ++k) v[k] = 0.0f;
-    int slot = 0;
-    if (act) {
-      j = (int)(e0.x & PAIR_J_MASK);
-      const int pl = (int)((e0.x >> 25) & 31u);
-      const float G = __uint_as_float(e0.y), Tb = __uint_as_float(e0.z);
-      const float4 a = __ldg(slab + 3 * j), b = __ldg(slab + 3 * j + 1), cc = __ldg(slab + 3 * j + 2);
-      slot = __float_as_int(cc.z);
-      const float4 g = pgw[pl];
-      const float dx = a.x - (float)(bx + (pl & 7)), dy = a.y - (float)(by + (pl >> 3));
-      const float alpha = fminf(ALPHA_MAX, b.y * G);
-      const float qv = (b.z * g.x + b.w * g.y) + (cc.x * g.z + cc.y * g.w);
-      const float sg = (__uint_as_float(e0.w) * g.x + __uint_as_float(e1.x) * g.y) +
-                       (__uint_as_float(e1.y) * g.z + __uint_as_float(e1.z) * g.w);
-      const float dL_dalpha = Tb * qv - __fdividef(pqw[pl] - sg, 1.0f - alpha);
-      const float dL_dG = b.y * dL_dalpha;
-      const float gdx = G * dx, gdy = G * dy;
-      v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
-      v[1] = dL_dG * (-gdy * b.x - gdx * a.w);
-      v[2] = -0.5f * gdx * dx * dL_dG;
-      v[3] = -gdx * dy * dL_dG;
-      v[4] = -0.5f * gdy * dy * dL_dG;
-      v[5] = G * dL_dalpha;
-      const float w = alpha * Tb;
-      v[6] = w * g.x; v[7] = w * g.y; v[8] = w * g.z; v[9] = w * g.w;
-    }
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int jo = __shfl_down_sync(0xffffffffu, j, off);
-      const bool same = (lane + off < 32) && (jo == j) && (j >= 0);
-      if (!__any_sync(0xffffffffu, same)) break;
-#pragma unroll
-      for (int k = 0; k < 10; ++k) {
-        const float vo = __shfl_down_sync(0xffffffffu, v[k], off);
-        if (same) v[k] += vo;
+        for (int w = 0; w < 8; ++w) {
+          const float x0 = (float)(tx0 + (w & 1) * 8), y0 = (float)(ty0 + (w >> 1) * 4);
+          if (box_hits(bb, x0, x0 + 7.0f, y0, y0 + 3.0f)) mask |= 1u << w;
+        }
       }
+      const int nreg = __popc(mask);
+      const int need = nreg > 1 ? nreg : 0;
+      const int inc = warp_incl_scan_i(need, lane);
+      const int tot = __shfl_sync(0xffffffffu, inc, 31);
+      int wbase = 0;
+      if (lane == 0 && tot > 0) wbase = atomicAdd(&S.base, tot);   // slot POSITIONS may vary run to run; sums do not
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (r < wn) S.info[r] = mask | ((unsigned)(wbase + inc - need) << 8);
     }
-    const int jprev = __shfl_up_sync(0xffffffffu, j, 1);
-    if (act && (lane == 0 || jprev != j)) {          // run head: holds this warp's sums for record j
-      const unsigned info = S.info[j];
-      const unsigned mask = info & 0xffu;
-      if (__popc(mask) <= 1) {
-        float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
-        atomicOr(&S.wrote[j >> 5], 1u << (j & 31));
-      } else {
-        float* ex = S.exch[(info >> 8) + __popc(mask & ((1u << wid) - 1u))];
+    __syncthreads();
+    if (S.base > LOG_ESLOTS) {               // too many multi-region records: leave the tile to the recomputing kernel
+      if (tid == 0) st.pair_count[(size_t)t * 8] = -1;
+      return;
+    }
+
+    // ---- this warp's pairs whose record lies in the window
+    while (bi < nbatch) {
+      const int idx = (bi << 5) + lane;
+      if (idx + 96 < count) prefetch_l1(lp + 2 * (size_t)(idx + 96));
+      uint4 e0 = make_uint4(PAIR_SKIP, 0u, 0u, 0u), e1 = e0;
+      if (idx < count) { e0 = lp[2 * (size_t)idx]; e1 = lp[2 * (size_t)idx + 1]; }
+      // lanes at / after a SKIP marker (or past the end of the log) hold no pair
+      const unsigned skipm = __ballot_sync(0xffffffffu, (idx >= count) || (e0.x == PAIR_SKIP));
+      const int nv = skipm ? __ffs(skipm) - 1 : 32;
+      const int jraw = (int)(e0.x & PAIR_J_MASK);
+      const bool act = (lane < nv) && (jraw >= w0) && (jraw < wend);
+      const bool beyond = (lane < nv) && (jraw >= wend);          // sorted by record: belongs to a later window
+      const unsigned bym = __ballot_sync(0xffffffffu, beyond);
+      int j = -1;
+      float v[10];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) ex[k] = v[k];
+      for (int k = 0; k < 10; ++k) v[k] = 0.0f;
+      int slot = 0;
+      if (act) {
+        j = jraw - w0;
+        const int pl = (int)((e0.x >> 25) & 31u);
+        const float G = __uint_as_float(e0.y), Tb = __uint_as_float(e0.z);
+        const float4 a = S.rec[3 * j], b = S.rec[3 * j + 1], cc = S.rec[3 * j + 2];
+        slot = __float_as_int(cc.z);
+        const float4 g = pgw[pl];
+        const float dx = a.x - (float)(bx + (pl & 7)), dy = a.y - (float)(by + (pl >> 3));
+        const float alpha = fminf(ALPHA_MAX, b.y * G);
+        const float qv = (b.z * g.x + b.w * g.y) + (cc.x * g.z + cc.y * g.w);
+        const float sg = (__uint_as_float(e0.w) * g.x + __uint_as_float(e1.x) * g.y) +
+                         (__uint_as_float(e1.y) * g.z + __uint_as_float(e1.z) * g.w);
+        const float dL_dalpha = Tb * qv - __fdividef(pqw[pl] - sg, 1.0f - alpha);
+        const float dL_dG = b.y * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
+        v[1] = dL_dG * (-gdy * b.x - gdx * a.w);
+        v[2] = -0.5f * gdx * dx * dL_dG;
+        v[3] = -gdx * dy * dL_dG;
+        v[4] = -0.5f * gdy * dy * dL_dG;
+        v[5] = G * dL_dalpha;
+        const float w = alpha * Tb;
+        v[6] = w * g.x; v[7] = w * g.y; v[8] = w * g.z; v[9] = w * g.w;
       }
-    }
-    p0 += ncomp;
-    e0 = n0; e1 = n1;
-  }
-  __syncthreads();
-  // multi-region records: add the regions' sums in region order; untouched single-region records: zeros
-  for (int r = tid; r < L; r += TILE_THREADS) {
-    const unsigned info = S.info[r];
-    const int nreg = __popc(info & 0xffu);
-    float v[10];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) v[k] = 0.0f;
-    if (nreg > 1) {
-      const float* ex = S.exch[info >> 8];
-      for (int o = 0; o < nreg; ++o)
+      for (int off = 1; off < 32; off <<= 1) {
+        const int jo = __shfl_down_sync(0xffffffffu, j, off);
+        const bool same = (lane + off < 32) && (jo == j) && (j >= 0);
+        if (!__any_sync(0xffffffffu, same)) break;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] += ex[o * 10 + k];
-    } else if ((S.wrote[r >> 5] >> (r & 31)) & 1u) {
-      continue;
+        for (int k = 0; k < 10; ++k) {
+          const float vo = __shfl_down_sync(0xffffffffu, v[k], off);
+          if (same) v[k] += vo;
+        }
+      }
+      const int jprev = __shfl_up_sync(0xffffffffu, j, 1);
+      if (act && (lane == 0 || jprev != j)) {          // run head: holds this warp's sums for record j
+        const unsigned info = S.info[j];
+        const unsigned mask = info & 0xffu;
+        if (__popc(mask) <= 1) {
+          float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+          atomicOr(&S.wrote[j >> 5], 1u << (j & 31));
+        } else {
+          float* ex = S.exch[(info >> 8) + __popc(mask & ((1u << wid) - 1u))];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) ex[k] = v[k];
+        }
+      }
+      if (bym) break;                      // the rest of this batch belongs to a later window: revisit it there
+      ++bi;
     }
-    const int slot = __float_as_int(__ldg(reinterpret_cast<const float*>(slab + 3 * r + 2) + 2));
-    float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-    *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+    __syncthreads();
+    // ---- window epilogue: multi-region records: add the regions' sums in region order; untouched single-region
+    // records: zeros
+    for (int r = tid; r < wn; r += TILE_THREADS) {
+      const unsigned info = S.info[r];
+      const int nreg = __popc(info & 0xffu);
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] = 0.0f;
+      if (nreg > 1) {
+        const float* ex = S.exch[info >> 8];
+        for (int o = 0; o < nreg; ++o)
+#pragma unroll
+          for (int k = 0; k < 10; ++k) v[k] += ex[o * 10 + k];
+      } else if ((S.wrote[r >> 5] >> (r & 31)) & 1u) {
+        continue;
+      }
+      const int slot = __float_as_int(reinterpret_cast<const float*>(&S.rec[3 * r + 2])[2]);
+      float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+    }
+    if (w0 + LOG_W < L) __syncthreads();     // the next window re-initialises the shared tables
   }
 }
 
@@ -863,8 +880,11 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
   }
   const bool use_log = st.pair_log != nullptr && st.pair_count != nullptr && d.pair_cap > 0;
   if (use_log) {
-    blend_backward_log_kernel<<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
-    cudaError_t e0 = cudaGetLastError();
+    cudaError_t e0 = cudaFuncSetAttribute(blend_backward_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(LogSmem));
+    if (e0 != cudaSuccess) return e0;
+    blend_backward_log_kernel<<<grid, TILE_THREADS, sizeof(LogSmem), s>>>(d, in.bg, st, gout, gin.dup_grad);
+    e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
   }
   const size_t smem = sizeof(BwdSmem);

@@ -54,6 +54,8 @@ int check_desc(const SpfRasterDesc* desc) {
     return fail(SPF_ERR_BAD_ARG, "dup_capacity must be in 1..2^31-1");
   if ((int64_t)desc->n_scenes * desc->views_per_scene > 65535)
     return fail(SPF_ERR_UNSUPPORTED, "more than 65535 views per call");
+  if (desc->pair_capacity < 0 || (desc->pair_capacity & 31))
+    return fail(SPF_ERR_BAD_ARG, "pair_capacity must be a non-negative multiple of 32");
   if (desc->flags & SPF_FLAG_DEPTH_NORMALIZED) return fail(SPF_ERR_UNSUPPORTED, "normalised depth not implemented");
   return 0;
 }

@@ -351,4 +351,10 @@ def profile_stages(settings: RasterSettings, means, scales, rotations, opacities
                 acc[n] += e0.elapsed_time(e1)
     out = {n: acc[n] / iters for n in acc}
     out["_n_dups"] = st.n_dups
+    if "pair_count" in st.tensors:
+        pc = st.tensors["pair_count"].view(-1, 8)
+        out["_pair_cap"] = int(st.desc.pair_capacity)
+        out["_pair_need"] = int(st.tensors["control"][2])
+        out["_fallback_tiles"] = int((pc < 0).any(dim=1).sum())
+        out["_tiles"] = int(pc.shape[0])
     return out

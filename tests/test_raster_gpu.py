@@ -254,6 +254,14 @@ def test_pair_log_counts_and_capacity_feedback():
         if c == 0:
             continue
         w0 = log[wi, :c, 0].to(torch.int64) & 0xFFFFFFFF
+        # runs never straddle a 32-record block: the rest of a block after a SKIP marker (0xffffffff) is padding
+        keep = torch.ones(c, dtype=torch.bool)
+        for blk in range(0, c, 32):
+            mk = (w0[blk:blk + 32] == 0xFFFFFFFF).nonzero()
+            if mk.numel():
+                keep[blk + int(mk[0]):blk + 32] = False
+        w0 = w0[keep]
+        c = int(keep.sum())
         j = w0 & ((1 << 25) - 1)
         lane = (w0 >> 25) & 31
         tile, wid = wi // 8, wi % 8
