@@ -100,21 +100,35 @@ emit_kernel(Dims d, SpfRasterState st, const int* __restrict__ block_off, const 
   int woff = 0;
   for (int w = 0; w < wid; ++w) woff += warp_part[w];
   const int slot0 = block_off[(size_t)view * d.NB + blockIdx.x] + woff + inc - tiles;
-  if (g >= d.P) return;
-  st.dup_offset[vg] = slot0;
-  if (tiles == 0) return;
-  const float2 p = reinterpret_cast<const float2*>(st.xy)[vg];
-  int rx0, ry0, rx1, ry1;
-  rect_of(p.x, p.y, st.radii[vg], d.gx, d.gy, rx0, ry0, rx1, ry1);
-  const uint64_t entry = ((uint64_t)__float_as_uint(st.depth[vg]) << 32) | (uint32_t)g;
-  const size_t tbase = (size_t)view * d.T;
-  for (int y = ry0; y < ry1; ++y)
-    for (int x = rx0; x < rx1; ++x) {
-      const size_t t = tbase + y * d.gx + x;
-      const int64_t pos = (int64_t)tile_start[t] + atomicAdd(tile_cursor + t, 1);
+  int rx0 = 0, ry0 = 0, rx1 = 1, ry1 = 0;
+  uint64_t entry = 0;
+  if (g < d.P) {
+    st.dup_offset[vg] = slot0;
+    if (tiles > 0) {
+      const float2 p = reinterpret_cast<const float2*>(st.xy)[vg];
+      rect_of(p.x, p.y, st.radii[vg], d.gx, d.gy, rx0, ry0, rx1, ry1);
+      entry = ((uint64_t)__float_as_uint(st.depth[vg]) << 32) | (uint32_t)g;
+    }
+  }
+  // one bucket slot per touched tile, claimed with warp-aggregated atomics on the tile cursors
+  int* cursor = tile_cursor + (size_t)view * d.T;
+  const int* tstart = tile_start + (size_t)view * d.T;
+  int maxc = tiles;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+  const int cw = rx1 - rx0;
+  int x = 0, y = 0;
+  for (int k = 0; k < maxc; ++k) {
+    const bool has = k < tiles;
+    const int t = (ry0 + y) * d.gx + rx0 + x;
+    const int rank = warp_aggregated_add(has, cursor, t, lane);
+    if (has) {
+      const int64_t pos = (int64_t)tstart[t] + rank;
       if (pos < d.cap) st.bucket[pos] = entry;
       else *overflow = 1;
     }
+    if (++x == cw) { x = 0; ++y; }
+  }
 }
 
 cudaError_t launch_emit(const Dims& d, const SpfRasterState& st, const ControlLayout& cl, cudaStream_t s) {

@@ -73,7 +73,7 @@ project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restric
   }
   __syncthreads();
 
-  int tiles = 0;
+  int tiles = 0, cx0 = 0, cy0 = 0, cw = 1;
   if (g < d.P) {
     Projected o;
     const bool vis = project_forward(vc, m, s, q, o);
@@ -105,10 +105,19 @@ project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restric
     st.rgb[vg * 3 + 0] = rgb[0]; st.rgb[vg * 3 + 1] = rgb[1]; st.rgb[vg * 3 + 2] = rgb[2];
     st.radii[vg] = o.radius;
     st.tiles_touched[vg] = o.tiles;
-    if (vis) {
-      int* tc = tile_count + (size_t)view * d.T;
-      for (int y = o.ry0; y < o.ry1; ++y)
-        for (int x = o.rx0; x < o.rx1; ++x) atomicAdd(tc + y * d.gx + x, 1);
+    if (vis) { cx0 = o.rx0; cy0 = o.ry0; cw = o.rx1 - o.rx0; }
+  }
+  // per-tile duplicate counts: warp-aggregated atomics over the cells of every lane's tile rectangle
+  {
+    int* tc = tile_count + (size_t)view * d.T;
+    int maxc = tiles;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+    int x = 0, y = 0;
+    for (int k = 0; k < maxc; ++k) {
+      const bool has = k < tiles;
+      warp_aggregated_add(has, tc, (cy0 + y) * d.gx + cx0 + x, tid & 31);
+      if (++x == cw) { x = 0; ++y; }
     }
   }
   // block total of tiles_touched (for the duplicate-slot prefix sums)

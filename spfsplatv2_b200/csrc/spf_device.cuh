@@ -66,6 +66,25 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+// ---- warp-aggregated atomics ------------------------------------------------------------------
+// Every lane of the warp calls this (has = false for lanes with nothing to add).  Lanes that target the same counter
+// are grouped with match.any; only the group leader issues the atomic.  Neighbouring Gaussians (one per context pixel,
+// raster order) land in the same one or two tiles, so this removes ~10x of the same-address L2 atomics.
+// Returns the value of the counter before the group's add, plus this lane's rank inside its group.
+__device__ __forceinline__ int warp_aggregated_add(bool has, int* counters, int key, int lane) {
+  const unsigned act = __ballot_sync(0xffffffffu, has);
+  int pos = 0;
+  if (has) {
+    const unsigned peers = __match_any_sync(act, key);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counters + key, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    pos = base + __popc(peers & ((1u << lane) - 1u));
+  }
+  return pos;
+}
+
 // ---- reductions ------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
