@@ -344,8 +344,9 @@ static cudaError_t launch_tsp(const Dims& d, const SpfRasterState& st, const Con
 cudaError_t launch_tile_sort_pack(const Dims& d, const SpfRasterState& st, const ControlLayout& cl,
                                   cudaStream_t s) {
   // shared-memory variant from the expected list length: dup_capacity is the caller's high-water mark of the
-  // duplicate count, so cap / tiles over-estimates the mean list; twice that covers the spread between tiles
-  const int64_t want = 2 * d.cap / ((int64_t)d.B * d.T);
+  // duplicate count (about 1.5 x N), so cap / tiles over-estimates the mean list; about twice the mean covers the
+  // spread between tiles (longer lists still work: in-place global sort)
+  const int64_t want = 4 * d.cap / (3 * (int64_t)d.B * d.T);   // cap ~ 1.5 x N  ->  ~2 x the mean list length
   if (want <= 2048) return launch_tsp<2048, 2048>(d, st, cl, s);     // 24 KB
   if (want <= 4096) return launch_tsp<4096, 4096>(d, st, cl, s);     // 48 KB
   return launch_tsp<8192, 8192>(d, st, cl, s);                       // 96 KB

@@ -25,7 +25,7 @@ PROJ_THREADS = 128
 # are sized from a per-shape high-water mark; the exact count N comes back through pinned memory while
 # the blend kernel is already running, and the forward is re-run (rare) if N exceeded the capacity.
 _capacity_hint: dict = {}
-GROWTH = 1.25
+GROWTH = 1.5
 _host_counters: dict = {}     # device index -> (pinned int32[2] tensor, numpy view)
 _ticket = [0]
 # Pair-log sizing (records per warp): per-shape high-water mark of control[2], fed back asynchronously after each
@@ -37,21 +37,16 @@ PAIR_CAP_DEFAULT = 512
 PAIR_LOG_BUDGET = 4 << 30     # bytes; above this the capacity is clipped and the densest tiles fall back to recomputation
 
 
-def _counters(dev):
-    hc = _host_counters.get(dev.index)
-    if hc is None:
-        t = torch.zeros(2, dtype=torch.int32).pin_memory()
-        hc = (t, t.numpy())
-        _host_counters[dev.index] = hc
-    return hc
-
-
 def _ptr(t: Optional[Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
 def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _raw_stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _f32c(t: Tensor) -> Tensor:
@@ -76,6 +71,7 @@ class RasterSettings:
     no_tma: bool = False
     bwd_v1: bool = False                # debugging: first-generation blend backward
     pair_log: bool = True               # forward logs contributing pairs for the backward (when grads are needed)
+    sync_count: bool = False            # always wait for the duplicate count in the forward (never defer the check)
 
     def flags(self) -> int:
         f = 0
@@ -94,9 +90,109 @@ class RasterSettings:
         return f
 
 
+class _Workspace:
+    """All forward intermediates in ONE device allocation (one caching-allocator call instead of ~20); raw pointers are
+    base + offset, tensor views are only materialised on demand (tests / inspection)."""
+    _SIZES = {torch.float32: 4, torch.int32: 4, torch.int64: 8}
+
+    def __init__(self, device, spec):
+        self.layout = {}
+        off = 0
+        for name, shape, dtype in spec:
+            n = 1
+            for d in shape:
+                n *= int(d)
+            self.layout[name] = (off, tuple(int(d) for d in shape), dtype, n)
+            off += (n * self._SIZES[dtype] + 255) // 256 * 256
+        self.buf = torch.empty(max(off, 256), dtype=torch.uint8, device=device)
+        self.base = self.buf.data_ptr()
+        self._views = {}
+
+    def ptr(self, name):
+        ent = self.layout.get(name)
+        return None if ent is None else C.c_void_p(self.base + ent[0])
+
+    def __contains__(self, name):
+        return name in self.layout
+
+    def get(self, name, default=None):
+        return self[name] if name in self.layout else default
+
+    def __getitem__(self, name):
+        v = self._views.get(name)
+        if v is None:
+            off, shape, dtype, n = self.layout[name]
+            v = self.buf[off:off + n * self._SIZES[dtype]].view(dtype).view(shape)
+            self._views[name] = v
+        return v
+
+
+class _Tensors:
+    """dict-like view over the state's workspaces (fixed-size one + capacity-dependent one)."""
+
+    def __init__(self, *spaces):
+        self.spaces = spaces
+
+    def __contains__(self, name):
+        return any(name in w for w in self.spaces)
+
+    def __getitem__(self, name):
+        for w in self.spaces:
+            if name in w:
+                return w[name]
+        raise KeyError(name)
+
+    def ptr(self, name):
+        for w in self.spaces:
+            if name in w:
+                return w.ptr(name)
+        return None
+
+
+_STATE_FIELDS = ("xy", "depth", "conic_opacity", "rgb", "radii", "tiles_touched", "dup_offset", "control", "bucket",
+                 "slab", "cullbox", "tile_ranges", "final_T", "n_contrib", "accum", "pair_log", "pair_count")
+
+N_COUNTER_SLOTS = 16
+
+
+def _counters(dev):
+    """Ring of {N, ticket} slots in mapped pinned host memory (one slot per in-flight forward)."""
+    hc = _host_counters.get(dev.index)
+    if hc is None:
+        t = torch.zeros(N_COUNTER_SLOTS, 2, dtype=torch.int32).pin_memory()
+        hc = (t, t.numpy())
+        _host_counters[dev.index] = hc
+    return hc
+
+
 class _State:
-    """Forward intermediates kept for backward / inspection (plain tensors, not autograd-tracked)."""
-    __slots__ = ("desc", "cin", "cstate", "keep", "n_dups", "capacity", "tensors", "key")
+    """Forward intermediates kept for backward / inspection (not autograd-tracked)."""
+    __slots__ = ("desc", "cin", "cstate", "cout", "keep", "_n_dups", "capacity", "tensors", "key", "ticket", "slot",
+                 "dev", "settings", "scratch")
+
+    @property
+    def n_dups(self) -> int:
+        """Duplicate count of this forward.  Read from the pinned slot the scan kernel wrote; normally long there by
+        the time anyone asks (the polling loop only waits if the GPU has not reached the scan kernel yet)."""
+        if self._n_dups is None:
+            self._n_dups = _wait_count(self.dev, self.slot, self.ticket, self.tensors)
+        return self._n_dups
+
+
+def _wait_count(dev, slot, ticket, tensors) -> int:
+    _, host_np = _counters(dev)
+    spins = 0
+    while True:
+        cur = int(host_np[slot, 1])
+        if cur == ticket:
+            return int(host_np[slot, 0])
+        if cur > ticket and (cur - ticket) % N_COUNTER_SLOTS == 0:
+            return int(tensors["control"][0])      # slot recycled by a later forward: ask the device (rare)
+        spins += 1
+        if spins > 2_000_000 and (spins & 0xfffff) == 0:
+            torch.cuda.current_stream(dev).synchronize()   # surfaces a launch failure instead of hanging
+            if int(host_np[slot, 1]) != ticket and spins > 20_000_000:
+                raise RuntimeError("spf_raster_forward: duplicate count never arrived (kernel failure?)")
 
 
 PAIR_FEEDBACK_LAG = 2   # forwards between a backward's report and its use
@@ -123,8 +219,30 @@ def _pair_capacity(key, n_warps: int) -> int:
     return max(64, min(cap, (PAIR_LOG_BUDGET // (32 * max(n_warps, 1))) // 64 * 64))
 
 
+def _launch_forward(st: "_State", fixed: _Workspace, cap: int, color, depth, alpha):
+    """(Re)allocate the capacity-dependent buffers for `cap` duplicates and enqueue the whole forward sequence."""
+    lib = L.lib()
+    dev = st.dev
+    capws = _Workspace(dev, [("bucket", (cap,), torch.int64), ("slab", (cap, 12), torch.float32),
+                             ("cullbox", (cap, 4), torch.float32)])
+    st.tensors = _Tensors(fixed, capws)
+    host_t, _ = _counters(dev)
+    _ticket[0] = (_ticket[0] % 0x3fffffff) + 1
+    st.ticket = _ticket[0]
+    st.slot = st.ticket % N_COUNTER_SLOTS
+    st.desc.dup_capacity = cap
+    st.desc.ticket = st.ticket
+    st.capacity = cap
+    st._n_dups = None
+    ptrs = [st.tensors.ptr(k) for k in _STATE_FIELDS]
+    st.cstate = L.SpfRasterState(*ptrs, C.c_void_p(host_t.data_ptr() + 8 * st.slot))
+    st.cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
+    L.check(lib.spf_raster_forward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(st.cout),
+                                   _stream(dev)), "spf_raster_forward")
+
+
 def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg,
-                  pre_scale, pair_log: bool = False):
+                  pre_scale, pair_log: bool = False, defer_count: bool = False):
     lib = L.lib()
     dev = means.device
     if dev.type != "cuda":
@@ -143,68 +261,46 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     if use_sh:
         K = shs.shape[-1] if s.sh_layout_ck else shs.shape[-2]
 
-    f32 = dict(dtype=torch.float32, device=dev)
-    i32 = dict(dtype=torch.int32, device=dev)
+    f32, i32 = torch.float32, torch.int32
     key = (dev.index, S, v, P, H, W)
-    cap = max(int(_capacity_hint.get(key, 2 * B * P)), 1024)
+    hint = _capacity_hint.get(key)
+    cap = max(int(hint if hint is not None else 2 * B * P), 1024)
 
     pair_cap = _pair_capacity(key, B * T * 8) if (pair_log and s.pair_log) else 0
-    desc = L.SpfRasterDesc(S, v, P, H, W, s.sh_degree, s.flags(), float(s.scale_modifier), cap, 0, pair_cap)
-    n_ctrl = lib.spf_raster_control_ints(C.byref(desc))
+    st = _State()
+    st.dev, st.key, st.settings = dev, key, s
+    st.desc = L.SpfRasterDesc(S, v, P, H, W, s.sh_degree, s.flags(), float(s.scale_modifier), cap, 0, pair_cap)
+    n_ctrl = lib.spf_raster_control_ints(C.byref(st.desc))
     if n_ctrl < 0:
         L.check(-1, "spf_raster_control_ints")
-
-    cin = L.SpfRasterIn(_ptr(means), _ptr(scales), _ptr(rots), _ptr(opac), _ptr(shs), _ptr(colors), K,
-                        _ptr(viewmat), _ptr(projmat), _ptr(tanfov), _ptr(bg), _ptr(pre_scale))
-    t = dict(
-        xy=torch.empty(B, P, 2, **f32), depth=torch.empty(B, P, **f32), conic_opacity=torch.empty(B, P, 4, **f32),
-        rgb=torch.empty(B, P, 3, **f32), radii=torch.empty(B, P, **i32), tiles_touched=torch.empty(B, P, **i32),
-        dup_offset=torch.empty(B, P, **i32), control=torch.empty(n_ctrl, **i32),
-        tile_ranges=torch.empty(B * T, 2, **i32), final_T=torch.empty(B, H, W, **f32),
-        n_contrib=torch.empty(B, H, W, **i32), accum=torch.empty(B, H, W, 4, **f32))
-    if pair_cap > 0:
-        t["pair_log"] = torch.empty(B * T * 8, pair_cap, 8, **f32)
-        t["pair_count"] = torch.empty(B * T * 8, **i32)
-    color = torch.empty(B, 3, H, W, **f32)
-    depth = torch.empty(B, 1, H, W, **f32)
-    alpha = torch.empty(B, 1, H, W, **f32) if s.want_alpha else None
-    host_t, host_np = _counters(dev)
-    stream = _stream(dev)
-    while True:
-        _ticket[0] = (_ticket[0] % 0x3fffffff) + 1
-        ticket = _ticket[0]
-        desc.dup_capacity = cap
-        desc.ticket = ticket
-        t["bucket"] = torch.empty(cap, dtype=torch.int64, device=dev)
-        t["slab"] = torch.empty(cap, 12, **f32)
-        t["cullbox"] = torch.empty(cap, 4, **f32)
-        cstate = L.SpfRasterState(*[_ptr(t[k]) for k in ("xy", "depth", "conic_opacity", "rgb", "radii",
-                                                        "tiles_touched", "dup_offset", "control", "bucket",
-                                                        "slab", "cullbox", "tile_ranges", "final_T", "n_contrib", "accum")],
-                                  _ptr(t.get("pair_log")), _ptr(t.get("pair_count")), _ptr(host_t))
-        cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
-        L.check(lib.spf_raster_forward(C.byref(desc), C.byref(cin), C.byref(cstate), C.byref(cout), stream),
-                "spf_raster_forward")
-        # The scan kernel stores {N, ticket} into mapped pinned memory; poll for our ticket.  All kernels of
-        # this forward are already queued, so the GPU keeps running emit / sort / blend meanwhile.
-        spins = 0
-        while host_np[1] != ticket:
-            spins += 1
-            if spins > 2_000_000 and (spins & 0xfffff) == 0:
-                torch.cuda.current_stream(dev).synchronize()   # surfaces a launch failure instead of hanging
-                if host_np[1] != ticket:
-                    raise RuntimeError("spf_raster_forward: duplicate count never arrived (kernel failure?)")
-        n_dups = int(host_np[0])
-        if n_dups <= cap:
-            break
-        cap = int(n_dups * 1.05) + 1024
-    _capacity_hint[key] = max(int(n_dups * GROWTH) + 1024, 1024)
-
-    st = _State()
-    st.desc, st.cin, st.cstate, st.n_dups, st.capacity, st.tensors = desc, cin, cstate, n_dups, cap, t
-    st.key = key
+    st.cin = L.SpfRasterIn(_ptr(means), _ptr(scales), _ptr(rots), _ptr(opac), _ptr(shs), _ptr(colors), K,
+                           _ptr(viewmat), _ptr(projmat), _ptr(tanfov), _ptr(bg), _ptr(pre_scale))
     st.keep = (means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale)
-    return color, depth, alpha, t["radii"], st
+    spec = [("xy", (B, P, 2), f32), ("depth", (B, P), f32), ("conic_opacity", (B, P, 4), f32), ("rgb", (B, P, 3), f32),
+            ("radii", (B, P), i32), ("tiles_touched", (B, P), i32), ("dup_offset", (B, P), i32), ("control", (n_ctrl,), i32),
+            ("tile_ranges", (B * T, 2), i32), ("final_T", (B, H, W), f32), ("n_contrib", (B, H, W), i32),
+            ("accum", (B, H, W, 4), f32)]
+    if pair_cap > 0:
+        spec += [("pair_log", (B * T * 8, pair_cap, 8), f32), ("pair_count", (B * T * 8,), i32)]
+    fixed = _Workspace(dev, spec)
+    color = torch.empty(B, 3, H, W, dtype=f32, device=dev)
+    depth = torch.empty(B, 1, H, W, dtype=f32, device=dev)
+    alpha = torch.empty(B, 1, H, W, dtype=f32, device=dev) if s.want_alpha else None
+    _launch_forward(st, fixed, cap, color, depth, alpha)
+    if defer_count and hint is not None and not s.sync_count:
+        # Steady-state training call: the duplicate count is NOT awaited here (that would make the host wait for the
+        # GPU to reach this call's scan kernel on every step).  Capacity = GROWTH x the largest count seen so far for
+        # this shape; the count is verified when the backward starts (see _Rasterize.backward).
+        pass
+    else:
+        while True:
+            n = st.n_dups        # polls the pinned slot: the rest of the forward is already queued behind the scan
+            if n <= cap:
+                break
+            cap = int(n * 1.05) + 1024
+            _launch_forward(st, fixed, cap, color, depth, alpha)
+        _capacity_hint[key] = max(int(_capacity_hint.get(key, 0)), int(n * GROWTH) + 1024)
+    return color, depth, alpha, fixed["radii"], st
 
 
 class _Rasterize(torch.autograd.Function):
@@ -213,7 +309,8 @@ class _Rasterize(torch.autograd.Function):
                 bg, pre_scale, means2d):
         args = [None if a is None else _f32c(a.detach()) for a in
                 (means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale)]
-        color, depth, alpha, radii, st = _forward_impl(settings, *args, pair_log=any(ctx.needs_input_grad))
+        need_grad = any(ctx.needs_input_grad)
+        color, depth, alpha, radii, st = _forward_impl(settings, *args, pair_log=need_grad, defer_count=need_grad)
         ctx.settings = settings
         ctx.st = st
         ctx.shapes = (means.shape, scales.shape, rots.shape, opac.shape,
@@ -236,12 +333,25 @@ class _Rasterize(torch.autograd.Function):
         B = S * s.views_per_scene
         NB = (P + PROJ_THREADS - 1) // PROJ_THREADS
         f32 = dict(dtype=torch.float32, device=dev)
+        # deferred duplicate-count check (the forward did not wait for it)
+        n = st.n_dups
+        if n > st.capacity:
+            import warnings
+            warnings.warn(f"spfsplatv2_b200: {n} tile duplicates exceeded the buffer capacity {st.capacity} chosen from "
+                          "earlier calls; the forward image of this call dropped some Gaussians.  Re-running the forward "
+                          "with the exact size for the backward (capacity raised for later calls).")
+            B_, H_, W_ = st.desc.n_scenes * st.desc.views_per_scene, st.desc.image_height, st.desc.image_width
+            scratch = (torch.empty(B_, 3, H_, W_, **f32), torch.empty(B_, 1, H_, W_, **f32),
+                       torch.empty(B_, 1, H_, W_, **f32) if s.want_alpha else None)
+            st.scratch = scratch
+            _launch_forward(st, st.tensors.spaces[0], int(n * 1.05) + 1024, *scratch)
+            n = st.n_dups
+        _capacity_hint[st.key] = max(int(_capacity_hint.get(st.key, 0)), int(n * GROWTH) + 1024)
         gc = None if g_color is None else _f32c(g_color)
         gd = None if g_depth is None else _f32c(g_depth)
         ga = None if (g_alpha is None or not s.want_alpha) else _f32c(g_alpha)
         gout = L.SpfRasterGradOut(_ptr(gc), _ptr(gd), _ptr(ga))
-        dup_grad = torch.empty(max(st.n_dups, 1), 12, **f32)
-        pose_partial = torch.empty(B, NB, 16, **f32)
+        scratch = _Workspace(dev, [("dup_grad", (max(n, 1), 12), torch.float32), ("pose_partial", (B, NB, 16), torch.float32)])
         d_means = torch.empty_like(means)
         d_scales = torch.empty_like(scales)
         d_rots = torch.empty_like(rots)
@@ -250,8 +360,8 @@ class _Rasterize(torch.autograd.Function):
         d_cols = torch.empty_like(colors) if colors is not None else None
         d_view = torch.empty(B, 16, **f32)
         d_m2d = torch.empty(B, P, 3, **f32) if (s.want_means2d_grad and ctx.shapes[7] is not None) else None
-        gin = L.SpfRasterGradIn(_ptr(dup_grad), _ptr(pose_partial), _ptr(d_means), _ptr(d_scales), _ptr(d_rots),
-                                _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
+        gin = L.SpfRasterGradIn(scratch.ptr("dup_grad"), scratch.ptr("pose_partial"), _ptr(d_means), _ptr(d_scales),
+                                _ptr(d_rots), _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
         L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
                                         C.byref(gin), _stream(dev)), "spf_raster_backward")
         if st.desc.pair_capacity > 0 and len(_pair_stat.setdefault(st.key, [])) < 4:
