@@ -60,6 +60,17 @@ class GradAllReduce:
         if world == 1:
             self._views = []
             return
+        if len(grads) == 1 and grads[0].is_contiguous():
+            # a single tensor IS the bucket: reduce it in place
+            g = grads[0]
+            self._views = []
+            if self.stream is not None:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self.stream):
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            return
         total = sum(g.numel() for g in grads)
         self._ensure_bucket(total, grads[0].dtype)
         views, off = [], 0
