@@ -245,6 +245,13 @@ def run_ours(args):
             "tile_sort_pack": 140.0 * N,
         }
         top = max((k for k in st if k in algo), key=lambda k: st[k])
+        traffic = None
+        try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tj.get("workload") == args.workload:
+                traffic = tj["kernels"].get(top, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         achieved = algo[top] / (st[top] * 1e-3) / 1e9
         step_bytes = 1208.0 * P * b + 228.0 * N + 60.0 * HW * b
         kern_ms = sum(st.values())
@@ -262,7 +269,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
-                         "traffic": None, "kernel_ms": round(st[top], 4),
+                         "traffic": traffic, "kernel_ms": round(st[top], 4),
                          "kernel_share_of_step": round(st[top] / kern_ms, 3)},
             "stage_ms": {k: round(v, 4) for k, v in st.items()},
             "pair_log": pair_info,

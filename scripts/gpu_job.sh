@@ -1,7 +1,5 @@
 #!/usr/bin/env bash
-python bench.py --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench_full.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print({k: d[k] for k in ('value','ms_per_step','e2e','roofline','cpu_baseline','clocks','gpu_launches')})
-print(d['stage_ms'])"
-python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-400
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"blend_forward|blend_backward_log|project_forward|project_backward|tile_sort_pack|emit_kernel" -s 30 -c 6 -o gpurun_out/prof_r1b -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_b.log 2>&1
+tail -2 gpurun_out/ncu_full_b.log | cut -c1-200
