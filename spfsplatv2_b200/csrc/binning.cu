@@ -28,10 +28,15 @@ __device__ void block_exclusive_scan(const int* __restrict__ in, int* __restrict
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int64_t base = 0; base < n; base += blockDim.x) {
-    const int64_t i = base + tid;
-    const int v = (i < n) ? in[i] : 0;
-    int inc = warp_incl_scan_i(v, lane);
+  // 4 consecutive elements per thread per round: 4096 per round with 1024 threads (the whole job in 1-2 rounds at
+  // the headline size instead of 8 barrier-separated ones)
+  for (int64_t base = 0; base < n; base += 4 * (int64_t)blockDim.x) {
+    const int64_t i0 = base + 4 * (int64_t)tid;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+    const int tsum = (v[0] + v[1]) + (v[2] + v[3]);
+    int inc = warp_incl_scan_i(tsum, lane);
     if (lane == 31) warp_part[wid] = inc;
     __syncthreads();
     if (wid == 0) {
@@ -41,10 +46,14 @@ __device__ void block_exclusive_scan(const int* __restrict__ in, int* __restrict
     }
     __syncthreads();
     const int carry = carry_s;
-    const int excl = carry + warp_part[wid] + inc - v;
-    if (i < n) out[i] = excl;
+    int excl = carry + warp_part[wid] + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) out[i0 + k] = excl;
+      excl += v[k];
+    }
     __syncthreads();
-    if (tid == blockDim.x - 1) carry_s = excl + v;
+    if (tid == blockDim.x - 1) carry_s = excl;
     __syncthreads();
   }
   if (tid == 0) {

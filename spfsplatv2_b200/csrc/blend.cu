@@ -184,7 +184,9 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   if (LOG) {
     if (lane == 0) {
       const int npairs = Cw - room;
-      st.pair_count[(size_t)t * 8 + (tid >> 5)] = (room >= 0 && L <= (int)PAIR_J_MASK) ? npairs : -1;
+      const bool okw = (room >= 0 && L <= (int)PAIR_J_MASK);
+      st.pair_count[(size_t)t * 8 + (tid >> 5)] = okw ? npairs : -1;
+      if (!okw) st.control[3] = 1;
       atomicMax(&blk_pairs, npairs);
     }
     __syncthreads();
@@ -643,6 +645,7 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
   const int n_tiles = d.B * d.T;
+  if (use_log && st.control[3] == 0) return;     // every tile was handled from the pair log
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     blend_backward_tile<TMA>(d, bg_all, st, go, dup_grad, use_log, S, t);
     __syncthreads();     // shared memory (incl. the mbarriers, re-initialised per tile) is reused by the next tile
@@ -765,7 +768,7 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
     }
     __syncthreads();
     if (S.base > LOG_ESLOTS) {               // too many multi-region records: leave the tile to the recomputing kernel
-      if (tid == 0) st.pair_count[(size_t)t * 8] = -1;
+      if (tid == 0) { st.pair_count[(size_t)t * 8] = -1; st.control[3] = 1; }
       return;
     }
 

@@ -215,32 +215,33 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
   }
 }
 
-// K9: dL/dviewmatrix[view] = fixed-order sum of block partials, campos gradient folded in.
+// K9: dL/dviewmatrix[view] = fixed-order sum of block partials, campos gradient folded in.  One CTA per view:
+// 15 components x 16 interleaved slices on 240 threads (independent, pipelined loads), then a 16-way fixed-order sum.
 __global__ void __launch_bounds__(256)
 pose_reduce_kernel(Dims d, const float* __restrict__ viewmatrix, const float* __restrict__ partial,
                    float* __restrict__ dV) {
-  __shared__ float red[256][16];
+  __shared__ float red[16][15];
   const int view = blockIdx.x, tid = threadIdx.x;
-  float acc[15];
-#pragma unroll
-  for (int i = 0; i < 15; ++i) acc[i] = 0.0f;
-  for (int b = tid; b < d.NB; b += 256) {
-    const float* p = partial + ((size_t)view * d.NB + b) * 16;
-#pragma unroll
-    for (int i = 0; i < 15; ++i) acc[i] += p[i];
+  const int c = tid % 15, part = tid / 15;
+  if (tid < 240) {
+    float a0 = 0.0f, a1 = 0.0f;
+    const float* p = partial + (size_t)view * d.NB * 16 + c;
+    int b = part;
+    for (; b + 16 < d.NB; b += 32) { a0 += __ldg(p + (size_t)b * 16); a1 += __ldg(p + (size_t)(b + 16) * 16); }
+    if (b < d.NB) a0 += __ldg(p + (size_t)b * 16);
+    red[part][c] = a0 + a1;
   }
-#pragma unroll
-  for (int i = 0; i < 15; ++i) red[tid][i] = acc[i];
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s)
-      for (int i = 0; i < 15; ++i) red[tid][i] += red[tid + s][i];
-    __syncthreads();
-  }
   if (tid == 0) {
+    float tot[15];
+    for (int i = 0; i < 15; ++i) {
+      float t = 0.0f;
+      for (int q = 0; q < 16; ++q) t += red[q][i];
+      tot[i] = t;
+    }
     float dA[9], dtau[3], dcam[3], V[16];
-    for (int i = 0; i < 9; ++i) dA[i] = red[0][i];
-    for (int i = 0; i < 3; ++i) { dtau[i] = red[0][9 + i]; dcam[i] = red[0][12 + i]; }
+    for (int i = 0; i < 9; ++i) dA[i] = tot[i];
+    for (int i = 0; i < 3; ++i) { dtau[i] = tot[9 + i]; dcam[i] = tot[12 + i]; }
     for (int i = 0; i < 16; ++i) V[i] = viewmatrix[view * 16 + i];
     fold_campos_grad(V, dcam, dA, dtau);
     float* o = dV + view * 16;

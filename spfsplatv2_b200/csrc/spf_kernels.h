@@ -13,18 +13,21 @@ constexpr int SORT_SMEM_CAP = 4096; // per-tile list length sorted in shared mem
 
 // control buffer layout (int32 words)
 struct ControlLayout {
-  int64_t n_total, overflow, tile_count, tile_cursor, tile_start, block_sum, block_off, total;
+  int64_t n_total, overflow, pair_max, need_fallback, tile_count, tile_cursor, tile_start, block_sum, block_off, pose_done, total;
 };
 inline ControlLayout control_layout(int B, int T, int NB) {
   ControlLayout c;
   c.n_total = 0;
   c.overflow = 1;
+  c.pair_max = 2;        // largest per-warp pair-log count needed (blend forward)
+  c.need_fallback = 3;   // some tile's pair log is unusable: the recomputing blend backward has work to do
   int64_t o = 4;
   c.tile_count = o;  o += (int64_t)B * T;
   c.tile_cursor = o; o += (int64_t)B * T;
   c.tile_start = o;  o += (int64_t)B * T + 1;
   c.block_sum = o;   o += (int64_t)B * NB;
   c.block_off = o;   o += (int64_t)B * NB + 1;
+  c.pose_done = o;   o += (int64_t)B;          // per-view counters of finished projection-backward blocks
   c.total = (o + 3) & ~int64_t(3);
   return c;
 }
