@@ -156,7 +156,7 @@ struct PFSmem {
   int warp_tot[2][PROJ_THREADS / 32];
 };
 
-__global__ void __launch_bounds__(PROJ_THREADS, 2)
+__global__ void __launch_bounds__(2 * PROJ_THREADS, 2)
 project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
                               int* __restrict__ block_sum) {
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
@@ -197,46 +197,48 @@ project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __
     const int sidx = k & 1;
     if (tid == 0 && item + (int)gridDim.x < total) issue(item + gridDim.x, sidx ^ 1);
     const int view = item / d.NB, chunk = item - view * d.NB;
-    const int g = chunk * PROJ_THREADS + tid;
+    const int role = tid >> 7, gi = tid & (PROJ_THREADS - 1);   // warps 0-3: geometry, warps 4-7: SH colour
+    const int g = chunk * PROJ_THREADS + gi;
     const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
     const ViewConsts& vc = S.vc[view];
     const PFStage& T = S.stage[sidx];
     mbar_wait(&S.full[sidx], (uint32_t)((k >> 1) & 1));
 
     int tiles = 0, cx0 = 0, cy0 = 0, cw = 1;
-    if (g < d.P) {
-      const size_t vg = (size_t)view * d.P + g;
+    const size_t vg = (size_t)view * d.P + g;
+    if (role == 1) {
+      if (g < d.P) {
+        float m[3];
+        for (int i = 0; i < 3; ++i) m[i] = T.means[gi * 3 + i] * ps;
+        const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
+        const float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
+        float pre[3];
+        sh_eval_fused(d.deg, dx * inv, dy * inv, dz * inv, T.sh + gi * row, sk, sc, pre);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float p5 = pre[c] + 0.5f;
+          st.rgb[vg * 3 + c] = (p5 < 0.0f) ? -0.0f : p5;     // sign bit = clamp mask for the backward
+        }
+      }
+    } else if (g < d.P) {
       float m[3], s[3], q[4];
-      for (int i = 0; i < 3; ++i) { m[i] = T.means[tid * 3 + i] * ps; s[i] = T.scales[tid * 3 + i] * ps; }
+      for (int i = 0; i < 3; ++i) { m[i] = T.means[gi * 3 + i] * ps; s[i] = T.scales[gi * 3 + i] * ps; }
       {
-        const float4 qq = T.rot[tid];
+        const float4 qq = T.rot[gi];
         if (d.flags & SPF_FLAG_QUAT_XYZW) { q[0] = qq.w; q[1] = qq.x; q[2] = qq.y; q[3] = qq.z; }
         else { q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w; }
       }
       Projected o;
       const bool vis = project_forward(vc, m, s, q, o);
       tiles = o.tiles;
-      float rgb[3];
-      {
-        const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
-        const float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
-        float pre[3];
-        sh_eval_fused(d.deg, dx * inv, dy * inv, dz * inv, T.sh + tid * row, sk, sc, pre);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float p5 = pre[c] + 0.5f;
-          rgb[c] = (p5 < 0.0f) ? -0.0f : p5;     // sign bit = clamp mask for the backward
-        }
-      }
       reinterpret_cast<float2*>(st.xy)[vg] = make_float2(o.px, o.py);
       st.depth[vg] = o.depth;
-      reinterpret_cast<float4*>(st.conic_opacity)[vg] = make_float4(o.conx, o.cony, o.conz, T.opac[tid]);
-      st.rgb[vg * 3 + 0] = rgb[0]; st.rgb[vg * 3 + 1] = rgb[1]; st.rgb[vg * 3 + 2] = rgb[2];
+      reinterpret_cast<float4*>(st.conic_opacity)[vg] = make_float4(o.conx, o.cony, o.conz, T.opac[gi]);
       st.radii[vg] = o.radius;
       st.tiles_touched[vg] = o.tiles;
       if (vis) { cx0 = o.rx0; cy0 = o.ry0; cw = o.rx1 - o.rx0; }
     }
-    {
+    if (role == 0) {
       int* tc = tile_count + (size_t)view * d.T;
       int maxc = tiles;
 #pragma unroll
@@ -249,7 +251,7 @@ project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __
       }
     }
     const int wsum = warp_sum_i(tiles);
-    if ((tid & 31) == 0) S.warp_tot[sidx][tid >> 5] = wsum;
+    if (role == 0 && (tid & 31) == 0) S.warp_tot[sidx][tid >> 5] = wsum;
     __syncthreads();     // stage sidx fully consumed (it is refilled two items later); warp totals visible
     if (tid == 0) {
       int t = 0;
@@ -285,7 +287,7 @@ cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const S
                                          (int)sizeof(PFSmem));
     if (e != cudaSuccess) return e;
     const int grid1 = min(d.B * d.NB, 2 * 148);
-    project_forward_stream_kernel<<<grid1, PROJ_THREADS, sizeof(PFSmem), s>>>(d, in, st, st.control + cl.tile_count,
+    project_forward_stream_kernel<<<grid1, 2 * PROJ_THREADS, sizeof(PFSmem), s>>>(d, in, st, st.control + cl.tile_count,
                                                                              st.control + cl.block_sum);
     return cudaGetLastError();
   }
