@@ -63,6 +63,30 @@ def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tens
     return view, proj, tanfov, scale
 
 
+def orthographic_setup(extrinsics: Tensor, width: Tensor, height: Tensor, near: Tensor, far: Tensor,
+                       fov_degrees: float = 0.1):
+    """Camera glue of the reference's ``render_cuda_orthographic`` (cuda_splatting.py:173-202): a tiny field of view with
+    the camera moved back so that the near plane is `width` wide.  Returns (viewmatrix [B,4,4], projmatrix [B,4,4],
+    tanfov [B,2], dump dict with the moved extrinsics / fov / near / far).  Batched where the reference only works
+    for B = 1 (it writes a [B] tensor into one matrix element)."""
+    b = extrinsics.shape[0]
+    dev = extrinsics.device
+    fov_x = torch.tensor(fov_degrees, device=dev).deg2rad()
+    tan_fov_x = (0.5 * fov_x).tan()
+    distance_to_near = (0.5 * width) / tan_fov_x
+    tan_fov_y = 0.5 * height / distance_to_near
+    fov_y = (2 * tan_fov_y).atan()
+    near = near + distance_to_near
+    far = far + distance_to_near
+    move_back = torch.eye(4, dtype=torch.float32, device=dev).repeat(b, 1, 1)
+    move_back[:, 2, 3] = -distance_to_near
+    extrinsics = extrinsics @ move_back
+    proj = get_projection_matrix(near, far, fov_x.expand(b), fov_y).transpose(1, 2)
+    view = torch.linalg.inv(extrinsics).transpose(1, 2)
+    tanfov = torch.stack([tan_fov_x.expand(b), tan_fov_y.expand(b)], dim=-1)
+    return view, proj, tanfov, dict(extrinsics=extrinsics, fov_x=fov_x, fov_y=fov_y, near=near, far=far)
+
+
 class _CameraSetupCUDA(torch.autograd.Function):
     """camera_setup as ONE kernel (csrc/camera.cu) with the pose-gradient path extrinsics <- viewmatrix."""
 

@@ -21,7 +21,7 @@ from typing import Literal, Optional
 import torch
 from torch import Tensor, nn
 
-from .camera import camera_setup_cuda, get_projection_matrix
+from .camera import camera_setup_cuda, get_projection_matrix, orthographic_setup
 from .rasterizer import RasterSettings, rasterize_batched
 
 DepthRenderingMode = Literal["depth", "log", "disparity", "relative_disparity"]
@@ -84,28 +84,10 @@ def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, 
                              fov_degrees: float = 0.1, use_sh: bool = True, dump: Optional[dict] = None,
                              enable_cov_grad: bool = False, enable_sh_grad: bool = False) -> Tensor:
     """Fake-orthographic render (tiny fov, camera moved back); returns images only, like the reference."""
-    b = extrinsics.shape[0]
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
-    dev = extrinsics.device
-    fov_x = torch.tensor(fov_degrees, device=dev).deg2rad()
-    tan_fov_x = (0.5 * fov_x).tan()
-    distance_to_near = (0.5 * width) / tan_fov_x
-    tan_fov_y = 0.5 * height / distance_to_near
-    fov_y = (2 * tan_fov_y).atan()
-    near = near + distance_to_near
-    far = far + distance_to_near
-    move_back = torch.eye(4, dtype=torch.float32, device=dev).repeat(b, 1, 1)
-    move_back[:, 2, 3] = -distance_to_near
-    extrinsics = extrinsics @ move_back
+    view, proj, tanfov, info = orthographic_setup(extrinsics, width, height, near, far, fov_degrees)
     if dump is not None:
-        dump["extrinsics"] = extrinsics
-        dump["fov_x"] = fov_x
-        dump["fov_y"] = fov_y
-        dump["near"] = near
-        dump["far"] = far
-    proj = get_projection_matrix(near, far, fov_x.expand(b), fov_y).transpose(1, 2)
-    view = torch.linalg.inv(extrinsics).transpose(1, 2)
-    tanfov = torch.stack([tan_fov_x.expand(b), tan_fov_y.expand(b)], dim=-1)
+        dump.update(info)
     color, _ = _render_views(view, proj, tanfov, None, image_shape, background_color, gaussian_means,
                              gaussian_sh_coefficients, gaussian_opacities, gaussian_rotations, gaussian_scales,
                              use_sh, enable_cov_grad, enable_sh_grad, 1)

@@ -8,6 +8,8 @@ Fixtures
   rope_ref.npz      outputs of the reference's rope_2d_cpu (curope.cpp:11-47, compiled unmodified into
                     oracle/_ref/curope_ref*.so) and of its pure-PyTorch RoPE2D fallback (pos_embed.py:112-159)
                     on seeded tokens / positions, forward (+F0) and backward (-F0).
+  ortho_ref.npz     the reference's render_cuda_orthographic (cuda_splatting.py:146-255) on a seeded box of Gaussians, same
+                    recording stand-in for the rasterizer: image + the arguments it passes (tensor-valued tanfov).
   decoder_ref.npz   the reference's UNMODIFIED DecoderSplattingCUDA.forward (decoder_splatting_cuda.py:41-78) and
                     render_cuda (cuda_splatting.py:45-144) driven end to end on a seeded scene, with the external
                     diff_gauss_pose package (absent) replaced by a recording module whose rasterizer
@@ -203,11 +205,47 @@ def make_decoder():
           f"proj contiguous={RECORD[0]['proj_contiguous']}, shs {RECORD[0]['shs_shape']}, opac {RECORD[0]['opac_shape']}")
 
 
+def make_orthographic():
+    """The reference's render_cuda_orthographic (cuda_splatting.py:146-255; B = 1, the only batch size its
+    `move_back[2, 3] = -distance_to_near` / [B]-shaped tanfovy arguments are sane for) on top of the oracle."""
+    _stub_modules()
+    RECORD.clear()
+    sys.modules["diff_gauss_pose"] = _fake_diff_gauss_pose()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from src.model.decoder.cuda_splatting import render_cuda_orthographic
+    g = torch.Generator().manual_seed(7)
+    P, h, w = 400, 48, 40
+    means = (torch.rand(1, P, 3, generator=g) - 0.5) * torch.tensor([2.4, 2.8, 2.0])
+    scales = 0.02 + 0.06 * torch.rand(1, P, 3, generator=g)
+    rot = torch.randn(1, P, 4, generator=g)
+    rot = rot / rot.norm(dim=-1, keepdim=True)
+    opac = torch.sigmoid(torch.randn(1, P, generator=g))
+    harm = torch.randn(1, P, 3, 25, generator=g) * 0.3
+    ext = torch.eye(4)[None].clone()
+    ext[0, :3, 3] = torch.tensor([0.1, -0.05, -3.0])
+    width, height = torch.tensor([3.0]), torch.tensor([3.6])
+    near, far = torch.tensor([0.5]), torch.tensor([20.0])
+    bg = torch.tensor([[0.1, 0.2, 0.3]])
+    dump = {}
+    img = render_cuda_orthographic(ext, width, height, near, far, (h, w), bg, means, torch.zeros(1, P, 3, 3), harm, opac,
+                                   rot, scales, fov_degrees=0.1, use_sh=True, dump=dump)
+    r = RECORD[0]
+    np.savez_compressed(os.path.join(HERE, "ortho_ref.npz"), means=means.numpy(), scales=scales.numpy(), rotations=rot.numpy(),
+                        opacities=opac.numpy(), harmonics=harm.numpy(), extrinsics=ext.numpy(), width=width.numpy(),
+                        height=height.numpy(), near=near.numpy(), far=far.numpy(), bg=bg.numpy(), image_shape=np.array([h, w]),
+                        image=img.detach().numpy(), rec_viewmatrix=r["viewmatrix"].numpy(), rec_projmatrix=r["projmatrix"].numpy(),
+                        rec_tanfov=np.array([float(r["tanfov"][0]), float(r["tanfov"][1])]),
+                        tanfov_types=np.array(r["tanfov_types"]), dump_near=dump["near"].numpy(), dump_far=dump["far"].numpy())
+    print(f"orthographic: image mean {img.mean().item():.4f}, tanfov types {r['tanfov_types']}, covered {(img[0] != bg.view(3,1,1)).any(0).float().mean():.2f}")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("make_golden.py needs /root/reference (run it in the build container)")
     make_rope()
     make_decoder()
+    make_orthographic()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

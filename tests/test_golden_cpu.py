@@ -105,3 +105,17 @@ def test_oracle_path_matches_reference_decoder_forward_backward(dec_gold):
     loss.backward()
     for k in ("means", "rotations", "scales", "harmonics", "opacities", "extrinsics"):
         assert rel_err(leaves[k].grad, torch.from_numpy(g["grad_" + k])) < 2e-6, k
+
+
+def test_orthographic_glue_matches_reference():
+    """orthographic_setup == the camera math of the reference's render_cuda_orthographic (cuda_splatting.py:173-202),
+    bit for bit, including the tensor-valued tanfov it hands to the rasterizer settings (:221-222)."""
+    from spfsplatv2_b200.camera import orthographic_setup
+    g = np.load(os.path.join(GOLD, "ortho_ref.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    view, proj, tanfov, info = orthographic_setup(t("extrinsics"), t("width"), t("height"), t("near"), t("far"), 0.1)
+    assert np.array_equal(view[0].numpy(), g["rec_viewmatrix"])
+    assert np.array_equal(proj[0].numpy(), g["rec_projmatrix"])
+    assert np.array_equal(tanfov[0].double().numpy(), g["rec_tanfov"])
+    assert list(g["tanfov_types"]) == ["Tensor", "Tensor"]          # the shim must coerce tensors to floats
+    assert np.array_equal(info["near"].numpy(), g["dump_near"]) and np.array_equal(info["far"].numpy(), g["dump_far"])

@@ -111,3 +111,32 @@ def test_cuda_decoder_matches_reference_decoder_golden():
     # tests/test_raster_gpu.py); the 1e-4 bar is enforced on bit-identical rasterizer inputs there.
     for k in t:
         assert rel_err(t[k].grad.cpu(), torch.from_numpy(g["grad_" + k])) < 1e-3, k
+
+
+def test_cuda_orthographic_matches_reference_golden():
+    """render_cuda_orthographic (figures path, a10 of SURVEY.md §8a) vs the reference's own function over the oracle;
+    also through the diff_gauss_pose shim with tensor-valued tanfov exactly as the reference passes them."""
+    from spfsplatv2_b200.decoder import render_cuda_orthographic
+    from spfsplatv2_b200.diff_gauss_pose import GaussianRasterizationSettings, GaussianRasterizer
+    g = np.load(os.path.join(GOLD, "ortho_ref.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(D0)
+    h, w = (int(x) for x in g["image_shape"])
+    P = g["means"].shape[1]
+    dump = {}
+    img = render_cuda_orthographic(t("extrinsics"), t("width"), t("height"), t("near"), t("far"), (h, w), t("bg"), t("means"),
+                                   torch.zeros(1, P, 3, 3, device=D0), t("harmonics"), t("opacities"), t("rotations"),
+                                   t("scales"), fov_degrees=0.1, use_sh=True, dump=dump)
+    want = torch.from_numpy(g["image"])
+    assert img.shape == want.shape
+    assert (img.cpu() - want).abs().max().item() < 5e-4      # fake-ortho: depths ~1.7e3, fp32 pixel positions ~1e-4 px
+    assert set(dump) == {"extrinsics", "fov_x", "fov_y", "near", "far"}
+    settings = GaussianRasterizationSettings(
+        image_height=h, image_width=w, tanfovx=torch.tensor(float(g["rec_tanfov"][0]), device=D0),
+        tanfovy=torch.tensor([float(g["rec_tanfov"][1])], device=D0), bg=t("bg")[0], scale_modifier=1.0,
+        projmatrix=t("rec_projmatrix").t().contiguous().t(), sh_degree=4, prefiltered=False, debug=False,
+        enable_cov_grad=False, enable_sh_grad=False)
+    image, depth, norm, alpha, radii, extra = GaussianRasterizer(settings)(
+        means3D=t("means")[0], means2D=torch.zeros(P, 3, device=D0), shs=t("harmonics")[0].permute(0, 2, 1).contiguous(),
+        colors_precomp=None, opacities=t("opacities")[0, :, None], scales=t("scales")[0], rotations=t("rotations")[0],
+        viewmatrix=t("rec_viewmatrix"))
+    assert (image.cpu() - want[0]).abs().max().item() < 5e-4
