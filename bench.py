@@ -110,11 +110,12 @@ def _make_inputs(workload: str, rank: int, pin: bool):
 
 def _step(dec, G, dev_in, leaves_keys=("means", "rotations", "scales", "harmonics", "opacities")):
     """One fwd+bwd of the decoder through the public API; returns the loss tensor."""
+    from spfsplatv2_b200.loss import mse_loss
     leaves = {k: dev_in[k].detach().requires_grad_() for k in leaves_keys}
     ext = dev_in["extrinsics"].detach().requires_grad_()
     g = G(leaves["means"], dev_in["cov"], leaves["rotations"], leaves["scales"], leaves["harmonics"], leaves["opacities"])
     out = dec(g, ext, dev_in["intrinsics"], dev_in["near"], dev_in["far"], dev_in["shape"])
-    loss = ((out.color - dev_in["gt"]) ** 2).mean()
+    loss = mse_loss(out.color, dev_in["gt"])      # fused MSE + dL/dcolor (src/loss/loss_mse.py:36-51)
     loss.backward()
     return loss, leaves, ext
 
@@ -212,6 +213,35 @@ def run_ours(args):
             ms, wall = float(t[0]), float(t[1])
         return ms, wall
 
+    # Steady-state loop as ONE CUDA graph (fwd + fused loss + bwd captured after eager warm-up steps have sized the
+    # data-dependent buffers): at this size the Python/autograd host path costs about as much as the GPU work, so
+    # the eager loop is launch-bound on slower hosts.  The all-reduce stays outside the graph on its side stream.
+    graphed = False
+    if not args.no_graph:
+        try:
+            for _ in range(max(args.warmup, 4)):
+                eager_loss = _step(dec, Gaussians, dev_in)[0]
+            torch.cuda.synchronize(dev)
+            eager_val = float(eager_loss)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = _step(dec, Gaussians, dev_in)[0]
+            graph.replay()
+            torch.cuda.synchronize(dev)
+            if abs(float(static_loss) - eager_val) > 1e-5 * max(1.0, abs(eager_val)):
+                raise RuntimeError(f"graph replay loss {float(static_loss)} != eager loss {eager_val}")
+
+            def step_resident():       # noqa: F811
+                graph.replay()
+                if world > 1:
+                    reducer.launch([ar_buf])
+                return static_loss
+            graphed = True
+        except Exception as exc:        # keep the eager loop
+            if rank == 0:
+                print(f"bench.py: CUDA-graph capture unavailable ({exc!r}); timing the eager loop", file=sys.stderr)
+            torch.cuda.synchronize(dev)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -262,10 +292,12 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {desc}", "views_per_step_per_gpu": b, "gaussians_per_scene": P,
                        "duplicates_per_step": N, "image": [h, w], "sh_degree": 4,
                        "parallelism": f"dp{world} (scenes sharded over ranks; 64 MiB stand-in grad all-reduce/step)" if world > 1 else "single GPU",
-                       "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step > 126 MB L2, no explicit flush"},
+                       "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step > 126 MB L2, no explicit flush",
+                       "loop": "one CUDA graph per step (fwd + fused MSE + bwd)" if graphed else "eager PyTorch loop",
+                       "loss": "fused MSE (spfsplatv2_b200.loss.mse_loss)"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(max(ms_e2e, wall_e2e) / args.steps, 4)},
-            "gpu_launches": 11 * args.steps,   # camera fwd/bwd, project fwd/bwd, scan, emit, sort+pack, blend fwd, blend bwd (log + fallback), pose reduce
+            "gpu_launches": 13 * args.steps,   # camera fwd/bwd, project fwd/bwd, scan, emit, sort+pack, blend fwd, blend bwd (log + fallback), pose reduce, fused MSE loss (2)
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
@@ -354,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager PyTorch loop instead of a captured CUDA graph")
     ap.add_argument("--cpu-views", type=int, default=4)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

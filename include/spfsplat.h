@@ -192,6 +192,16 @@ SPF_API int spf_camera_forward(int32_t B, int32_t scale_invariant, const float* 
 SPF_API int spf_camera_backward(int32_t B, int32_t scale_invariant, const float* near, const float* viewmatrix,
                         const float* dL_dviewmatrix, float* dL_dextrinsics, void* stream);
 
+/* Fused image losses on the rendered colour: per-image mean squared error of pred vs target, [n_images]
+ * images of n_per_image floats each, optionally after clipping both to [0,1] (clip != 0: the PSNR definition,
+ * src/evaluation/metrics.py:12-19).  If dL_dpred is not NULL it receives grad_scale * (pred - target) in the same pass
+ * (the MSE training loss of src/loss/loss_mse.py:36-51 is weight * mean_all, so grad_scale = 2 * weight / numel).
+ * partial: scratch of n_images * spf_image_mse_blocks(n_per_image) floats.  mse_per_image [n_images] and mean_all [1]
+ * may each be NULL.  Deterministic (no float atomics). */
+SPF_API int spf_image_mse_blocks(int64_t n_per_image);
+SPF_API int spf_image_mse(const float* pred, const float* target, int32_t n_images, int64_t n_per_image, int32_t clip,
+                  float grad_scale, float* dL_dpred, float* partial, float* mse_per_image, float* mean_all, void* stream);
+
 /* 2-D RoPE, in place.  Replaces rope_2d (curope.cpp:49-65).  tokens: [B,N,H,D] view with
  * stride(3)==1, stride(2)==D (kernels.cu:91); positions int64 [B,N,2] contiguous.
  * dtype: 0 = fp32, 1 = fp16, 2 = bf16.  fwd = +F0 forward, -F0 backward. */

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import _make_inputs, WORKLOADS
 from spfsplatv2_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg, Gaussians
+from spfsplatv2_b200.loss import mse_loss
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2p"
 v_cxt, h, w, b, _ = WORKLOADS[wl]
@@ -25,7 +26,7 @@ for it in range(N + 10):
     t1 = time.perf_counter()
     out = dec(g, ext, d["intrinsics"], d["near"], d["far"], (h, w))
     t2 = time.perf_counter()
-    loss = ((out.color - d["gt"]) ** 2).mean()
+    loss = mse_loss(out.color, d["gt"])
     t3 = time.perf_counter()
     loss.backward()
     t4 = time.perf_counter()
@@ -42,7 +43,7 @@ for it in range(30):
     ext = d["extrinsics"].detach().requires_grad_()
     g = Gaussians(leaves["means"], cov, leaves["rotations"], leaves["scales"], leaves["harmonics"], leaves["opacities"])
     out = dec(g, ext, d["intrinsics"], d["near"], d["far"], (h, w))
-    loss = ((out.color - d["gt"]) ** 2).mean()
+    loss = mse_loss(out.color, d["gt"])
     loss.backward()
 pr.disable()
 torch.cuda.synchronize()

@@ -55,7 +55,8 @@ class SpfRasterGradIn(C.Structure):
 
 EXPORTS = ("spf_version", "spf_last_error", "spf_raster_control_ints", "spf_raster_forward",
            "spf_raster_backward", "spf_raster_forward_stages", "spf_raster_backward_stages",
-           "spf_raster_unpack_sorted", "spf_camera_forward", "spf_camera_backward", "spf_rope2d")
+           "spf_raster_unpack_sorted", "spf_camera_forward", "spf_camera_backward", "spf_rope2d",
+           "spf_image_mse", "spf_image_mse_blocks")
 
 _lib = None
 
@@ -108,6 +109,11 @@ def lib() -> C.CDLL:
     l.spf_rope2d.restype = C.c_int
     l.spf_rope2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                              C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p]
+    l.spf_image_mse_blocks.restype = C.c_int
+    l.spf_image_mse_blocks.argtypes = [C.c_int64]
+    l.spf_image_mse.restype = C.c_int
+    l.spf_image_mse.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l
     return l
 

@@ -194,6 +194,25 @@ int spf_camera_backward(int32_t B, int32_t scale_invariant, const float* near, c
   return SPF_OK;
 }
 
+int spf_image_mse_blocks(int64_t n_per_image) {
+  int64_t b = (n_per_image / 4 + 4 * 256 - 1) / (4 * 256);      // ~4 float4 per thread
+  if (b < 1) b = 1;
+  if (b > 256) b = 256;
+  return (int)b;
+}
+
+int spf_image_mse(const float* pred, const float* target, int32_t n_images, int64_t n_per_image, int32_t clip,
+                  float grad_scale, float* dL_dpred, float* partial, float* mse_per_image, float* mean_all, void* stream) {
+  if (!pred || !target || !partial) return fail(SPF_ERR_BAD_ARG, "spf_image_mse: pred / target / partial are NULL");
+  if (n_images < 1 || n_images > 65535 || n_per_image < 1) return fail(SPF_ERR_BAD_ARG, "spf_image_mse: bad sizes");
+  if (!mse_per_image && n_images > 1024) return fail(SPF_ERR_BAD_ARG, "spf_image_mse: mse_per_image is required above 1024 images");
+  cudaError_t e = spf::launch_image_mse(pred, target, n_images, n_per_image, clip, grad_scale, dL_dpred, partial,
+                                        spf_image_mse_blocks(n_per_image), mse_per_image, mean_all,
+                                        static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "image_mse");
+  return SPF_OK;
+}
+
 int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
                int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
   if (!tokens || !positions) return fail(SPF_ERR_BAD_ARG, "tokens / positions are NULL");

@@ -61,6 +61,9 @@ cudaError_t launch_camera_forward(int B, int scale_invariant, const float* ext, 
                                   float* pre_scale, cudaStream_t s);
 cudaError_t launch_camera_backward(int B, int scale_invariant, const float* near, const float* view,
                                    const float* d_view, float* d_ext, cudaStream_t s);
+cudaError_t launch_image_mse(const float* pred, const float* target, int n_images, int64_t n_per_image, int clip,
+                             float grad_scale, float* dL_dpred, float* partial, int blocks_per_image,
+                             float* mse_per_image, float* mean_all, cudaStream_t s);
 cudaError_t launch_rope2d(void* tokens, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
                           int64_t sn, int dtype, float base, float fwd, cudaStream_t s);
 

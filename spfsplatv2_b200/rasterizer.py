@@ -168,7 +168,7 @@ def _counters(dev):
 class _State:
     """Forward intermediates kept for backward / inspection (not autograd-tracked)."""
     __slots__ = ("desc", "cin", "cstate", "cout", "keep", "_n_dups", "capacity", "tensors", "key", "ticket", "slot",
-                 "dev", "settings", "scratch")
+                 "dev", "settings", "scratch", "captured")
 
     @property
     def n_dups(self) -> int:
@@ -235,7 +235,8 @@ def _launch_forward(st: "_State", fixed: _Workspace, cap: int, color, depth, alp
     st.capacity = cap
     st._n_dups = None
     ptrs = [st.tensors.ptr(k) for k in _STATE_FIELDS]
-    st.cstate = L.SpfRasterState(*ptrs, C.c_void_p(host_t.data_ptr() + 8 * st.slot))
+    st.cstate = L.SpfRasterState(*ptrs, None if getattr(st, "captured", False)
+                                 else C.c_void_p(host_t.data_ptr() + 8 * st.slot))
     st.cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
     L.check(lib.spf_raster_forward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(st.cout),
                                    _stream(dev)), "spf_raster_forward")
@@ -265,10 +266,24 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     key = (dev.index, S, v, P, H, W)
     hint = _capacity_hint.get(key)
     cap = max(int(hint if hint is not None else 2 * B * P), 1024)
+    # CUDA-graph capture (torch.cuda.graph around a whole fwd+loss+bwd step): nothing here may wait on the GPU, and the
+    # sizes are frozen into the graph.  Run at least one eager step of the same shape first (it establishes the
+    # capacities); afterwards `graph_overflowed(state)` tells whether a replay ever outgrew them.
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing and hint is None:
+        raise RuntimeError("spfsplatv2_b200: run one eager forward of this shape before capturing it in a CUDA graph "
+                           "(the duplicate-buffer capacity is learned from it)")
 
-    pair_cap = _pair_capacity(key, B * T * 8) if (pair_log and s.pair_log) else 0
+    if pair_log and s.pair_log:
+        if capturing:
+            pair_cap = max(64, min(int(_pair_cap_hint.get(key, PAIR_CAP_DEFAULT)),
+                                   (PAIR_LOG_BUDGET // (32 * max(B * T * 8, 1))) // 64 * 64))
+        else:
+            pair_cap = _pair_capacity(key, B * T * 8)
+    else:
+        pair_cap = 0
     st = _State()
-    st.dev, st.key, st.settings = dev, key, s
+    st.dev, st.key, st.settings, st.captured = dev, key, s, capturing
     st.desc = L.SpfRasterDesc(S, v, P, H, W, s.sh_degree, s.flags(), float(s.scale_modifier), cap, 0, pair_cap)
     n_ctrl = lib.spf_raster_control_ints(C.byref(st.desc))
     if n_ctrl < 0:
@@ -287,7 +302,9 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     depth = torch.empty(B, 1, H, W, dtype=f32, device=dev)
     alpha = torch.empty(B, 1, H, W, dtype=f32, device=dev) if s.want_alpha else None
     _launch_forward(st, fixed, cap, color, depth, alpha)
-    if defer_count and hint is not None and not s.sync_count:
+    if capturing:
+        st._n_dups = cap            # sizes frozen at capture time
+    elif defer_count and hint is not None and not s.sync_count:
         # Steady-state training call: the duplicate count is NOT awaited here (that would make the host wait for the
         # GPU to reach this call's scan kernel on every step).  Capacity = GROWTH x the largest count seen so far for
         # this shape; the count is verified when the backward starts (see _Rasterize.backward).
@@ -335,7 +352,7 @@ class _Rasterize(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         # deferred duplicate-count check (the forward did not wait for it)
         n = st.n_dups
-        if n > st.capacity:
+        if (not st.captured) and n > st.capacity:
             import warnings
             warnings.warn(f"spfsplatv2_b200: {n} tile duplicates exceeded the buffer capacity {st.capacity} chosen from "
                           "earlier calls; the forward image of this call dropped some Gaussians.  Re-running the forward "
@@ -346,7 +363,8 @@ class _Rasterize(torch.autograd.Function):
             st.scratch = scratch
             _launch_forward(st, st.tensors.spaces[0], int(n * 1.05) + 1024, *scratch)
             n = st.n_dups
-        _capacity_hint[st.key] = max(int(_capacity_hint.get(st.key, 0)), int(n * GROWTH) + 1024)
+        if not st.captured:
+            _capacity_hint[st.key] = max(int(_capacity_hint.get(st.key, 0)), int(n * GROWTH) + 1024)
         gc = None if g_color is None else _f32c(g_color)
         gd = None if g_depth is None else _f32c(g_depth)
         ga = None if (g_alpha is None or not s.want_alpha) else _f32c(g_alpha)
@@ -364,7 +382,7 @@ class _Rasterize(torch.autograd.Function):
                                 _ptr(d_rots), _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
         L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
                                         C.byref(gin), _stream(dev)), "spf_raster_backward")
-        if st.desc.pair_capacity > 0 and len(_pair_stat.setdefault(st.key, [])) < 4:
+        if st.desc.pair_capacity > 0 and not st.captured and len(_pair_stat.setdefault(st.key, [])) < 4:
             # feed the largest per-warp pair count back to the sizing of the next forward (no wait)
             pin, ev = _pin_pool.pop() if _pin_pool else (torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
             pin.copy_(st.tensors["control"][2:3], non_blocking=True)
@@ -375,6 +393,13 @@ class _Rasterize(torch.autograd.Function):
                 None if d_shs is None else d_shs.view(sh[4]), None if d_cols is None else d_cols.view(sh[5]),
                 d_view.view(sh[6]), None, None, None, None,
                 None if d_m2d is None else d_m2d.view(sh[7]))
+
+
+def graph_overflowed(st: "_State") -> bool:
+    """After replaying a captured step: did any replay outgrow the duplicate buffer frozen into the graph (results of
+    that replay are then invalid: re-capture after an eager step), and how the pair log fared.  Synchronises."""
+    ctrl = st.tensors["control"][:4].cpu()
+    return bool(int(ctrl[0]) > st.capacity or int(ctrl[1]) != 0)
 
 
 def rasterize_batched(settings: RasterSettings, means: Tensor, scales: Tensor, rotations: Tensor,

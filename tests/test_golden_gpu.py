@@ -140,3 +140,35 @@ def test_cuda_orthographic_matches_reference_golden():
         colors_precomp=None, opacities=t("opacities")[0, :, None], scales=t("scales")[0], rotations=t("rotations")[0],
         viewmatrix=t("rec_viewmatrix"))
     assert (image.cpu() - want[0]).abs().max().item() < 5e-4
+
+
+def test_fused_image_losses_match_reference_definitions():
+    """spfsplatv2_b200.loss vs the reference's definitions (loss_mse.py:36-51, metrics.py:12-19) written out in torch:
+    value, dL/dcolor, PSNR; sizes that are / are not multiples of 4, strided inputs, loss weight, apply_after_step."""
+    from spfsplatv2_b200.loss import LossMse, LossMseCfg, compute_psnr, mse_loss
+    g = torch.Generator(device=D0).manual_seed(0)
+    for shape in [(2, 3, 3, 64, 48), (3, 1, 3, 17, 13), (1, 3, 5, 7)]:
+        pred = (torch.rand(shape, device=D0, generator=g) * 1.4 - 0.2).requires_grad_()
+        gt = torch.rand(shape, device=D0, generator=g)
+        ref_p = pred.detach().clone().requires_grad_()
+        ref = 0.7 * ((ref_p - gt) ** 2).mean()
+        ref.backward()
+        out = mse_loss(pred, gt, 0.7)
+        (out * 1.0).backward()
+        assert out.item() == pytest.approx(ref.item(), rel=2e-6)
+        assert torch.allclose(pred.grad, ref_p.grad, rtol=1e-6, atol=1e-9)
+        p4 = pred.detach().reshape(-1, *shape[-3:])
+        g4 = gt.reshape(-1, *shape[-3:])
+        want = -10 * ((g4.clip(0, 1) - p4.clip(0, 1)) ** 2).flatten(1).mean(1).log10()
+        assert torch.allclose(compute_psnr(g4, p4), want, rtol=1e-5, atol=1e-5)
+    loss = LossMse(LossMseCfg(weight=1.0, apply_after_step=5))
+    pred = torch.rand(2, 1, 3, 32, 32, device=D0, requires_grad=True)
+    gt = torch.rand(2, 1, 3, 32, 32, device=D0)
+    assert float(loss(pred, gt, None, 0)) == 0.0
+    v = loss(pred.transpose(-1, -2), gt.transpose(-1, -2), None, 10)       # non-contiguous views
+    assert v.item() == pytest.approx(((pred - gt) ** 2).mean().item(), rel=2e-6)
+    v.backward()
+    assert torch.allclose(pred.grad, 2 * (pred.detach() - gt) / pred.numel(), rtol=1e-6, atol=1e-9)
+    a = mse_loss(pred.detach(), gt)
+    b = mse_loss(pred.detach(), gt)
+    assert torch.equal(a, b)                                               # deterministic

@@ -413,3 +413,47 @@ def test_fused_camera_setup_matches_torch_glue():
         (ref[0] * wgt).sum().backward()
         (got[0] * wgt.to(d)).sum().backward()
         assert rel_err(e_gpu.grad.cpu(), e_cpu.grad) < 1e-5
+
+
+def test_cuda_graph_capture_of_a_whole_step():
+    """fwd + fused loss + bwd captured in ONE CUDA graph after an eager step has sized the data-dependent buffers;
+    replays reproduce the eager gradients bit for bit, and capturing a shape never seen eagerly is refused."""
+    from spfsplatv2_b200 import rasterizer as R
+    from spfsplatv2_b200.loss import mse_loss
+    d = _dev()
+    sc = make_batch(2, seed=47, v_cxt=1, h=64, w=64, grid=(40, 40), regime="trained", n_target=1)
+    dec = _decoder()
+    g, t = _gaussians(sc)
+    ext = sc.extrinsics.to(d)
+    gt = torch.rand(2, 1, 3, 64, 64, device=d)
+    K, near, far = sc.intrinsics.to(d), sc.near.to(d), sc.far.to(d)
+    from spfsplatv2_b200.decoder import Gaussians
+
+    def step():
+        leaves = {k: v.detach().requires_grad_() for k, v in t.items()}
+        e = ext.detach().requires_grad_()
+        gg = Gaussians(leaves["means"], g.covariances, leaves["rotations"], leaves["scales"], leaves["harmonics"], leaves["opacities"])
+        out = dec(gg, e, K, near, far, sc.image_shape)
+        loss = mse_loss(out.color, gt)
+        loss.backward()
+        return loss, leaves, e
+
+    R._capacity_hint.clear(); R._pair_cap_hint.clear(); R._pair_stat.clear()
+    graph = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="eager forward"):
+        with torch.cuda.graph(graph):
+            step()
+    torch.cuda.synchronize()
+    for _ in range(4):                       # eager steps: capacities (incl. the lagged pair-log feedback) settle
+        loss_e, leaves_e, ext_e = step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_g, leaves_g, ext_g = step()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(loss_g, loss_e.detach())
+    for k in leaves_e:
+        assert torch.equal(leaves_g[k].grad, leaves_e[k].grad), k
+    assert torch.equal(ext_g.grad, ext_e.grad)
