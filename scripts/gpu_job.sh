@@ -1,3 +1,2 @@
 #!/usr/bin/env bash
-python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-bash scripts/gpu_all_workloads.sh
+python -m pytest tests/test_raster_gpu.py -m gpu -q -x -k full_size 2>&1 | tail -25

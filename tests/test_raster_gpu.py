@@ -457,3 +457,66 @@ def test_cuda_graph_capture_of_a_whole_step():
     for k in leaves_e:
         assert torch.equal(leaves_g[k].grad, leaves_e[k].grad), k
     assert torch.equal(ext_g.grad, ext_e.grad)
+
+
+@pytest.mark.parametrize("v_cxt,h,w", [(2, 256, 256), (2, 512, 512)])     # BASELINE configs 2 and 4 at full size
+def test_full_size_properties(v_cxt, h, w):
+    """Size-independent properties at BASELINE.json's full sizes (the oracle takes minutes there):
+    keys sorted inside every tile and tile ranges partition the duplicate list; n_contrib within the tile list;
+    alpha in [0,1], colour = blended + T*bg; the backward is linear in the upstream gradient and bit-reproducible;
+    translation invariance ties the pose gradient to the mean gradients (sum_g dL/dm_g == dL/dtau A^T)."""
+    from spfsplatv2_b200.camera import camera_setup
+    from spfsplatv2_b200.rasterizer import RasterSettings, forward_with_state, rasterize_batched, unpack_sorted
+    d = _dev()
+    sc = make_scene(seed=53, v_cxt=v_cxt, h=h, w=w, regime="init", n_target=1)
+    view, proj, tanfov, scale = [x.to(d) for x in camera_setup(sc.extrinsics[0], sc.intrinsics[0], sc.near[0], sc.far[0], True)]
+    bg = torch.tensor([[0.2, 0.4, 0.6]], device=d)
+    s = RasterSettings(h, w, 4, 1.0, 1, sh_layout_ck=True, want_alpha=True)
+    base = (sc.means.to(d), sc.scales.to(d), sc.rotations.to(d), sc.opacities.to(d), sc.harmonics.to(d), None, view, proj, tanfov, bg, scale)
+    color, depth, alpha, radii, st = forward_with_state(s, *base)
+    N = st.n_dups
+    assert N == int(st.tensors["tiles_touched"].sum())
+    pl, keys = unpack_sorted(st)
+    rg = st.tensors["tile_ranges"].long()
+    T = rg.shape[0]
+    lens = rg[:, 1] - rg[:, 0]
+    assert int(lens.sum()) == N and int(lens.max()) > 0
+    nz = lens > 0
+    starts = rg[nz, 0]
+    assert torch.equal(torch.sort(starts).values, starts)                       # ranges in tile order ...
+    assert torch.equal(starts[1:], rg[nz, 1][:-1]) and int(starts[0]) == 0      # ... and contiguous: a partition
+    tile_of = keys >> 32
+    assert bool((tile_of[1:] >= tile_of[:-1]).all())                            # grouped by tile
+    same = tile_of[1:] == tile_of[:-1]
+    assert bool((keys[1:][same] >= keys[:-1][same]).all())                      # depth-sorted inside a tile
+    eq = same & ((keys[1:] & 0xFFFFFFFF) == (keys[:-1] & 0xFFFFFFFF))
+    assert bool((pl[1:][eq] > pl[:-1][eq]).all())                               # depth ties in Gaussian-id order
+    gx = (w + 15) // 16
+    tile_img = (torch.arange(h, device=d)[:, None] // 16) * gx + torch.arange(w, device=d)[None, :] // 16
+    assert bool((st.tensors["n_contrib"][0].long() <= lens[tile_img]).all())
+    assert float(alpha.min()) >= 0.0 and float(alpha.max()) <= 1.0
+    acc = st.tensors["accum"][0]
+    want = acc[..., :3].permute(2, 0, 1) + st.tensors["final_T"][0][None] * bg.view(3, 1, 1)
+    assert torch.allclose(color[0], want, rtol=0, atol=2e-7)        # the kernel fuses T*bg + C into one FMA
+    # backward: linearity, reproducibility, translation identity
+    gen = torch.Generator(device=d).manual_seed(2)
+    g1 = torch.randn(1, 3, h, w, device=d, generator=gen)
+    g2 = torch.randn(1, 3, h, w, device=d, generator=gen)
+
+    def grads(gc):
+        t = [x.clone().requires_grad_() for x in base[:5]]
+        vm = view.clone().requires_grad_()
+        c, dd, a, _ = rasterize_batched(s, t[0], t[1], t[2], t[3], t[4], None, vm, proj, tanfov, bg, scale)
+        c.backward(gc)
+        return [x.grad for x in t] + [vm.grad]
+    for _ in range(3):          # let the pair-log capacity settle (it changes which tiles use the log: different rounding)
+        grads(g1)
+    ga, gb, gab, ga2 = grads(g1), grads(g2), grads(g1 + 2.0 * g2), grads(g1)
+    for x, y in zip(ga, ga2):
+        assert torch.equal(x, y)
+    for x, y, z in zip(ga, gb, gab):
+        assert rel_err(z, x + 2.0 * y) < 2e-5
+    # means enter the rasterizer as m*scale: dL/dm = scale * dL/d(m*scale)  ->  undo the chain factor
+    lhs = ga[0][0].double().sum(0) / float(scale[0])
+    rhs = ga[5][0, 3, :3].double() @ view[0, :3, :3].double().t()
+    assert torch.allclose(lhs, rhs, rtol=2e-3, atol=2e-3 * float(lhs.abs().max()))
