@@ -1,2 +1,2 @@
 #!/usr/bin/env bash
-python -m pytest tests/test_raster_gpu.py -m gpu -q -x -k full_size 2>&1 | tail -25
+python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|error" | tail -3

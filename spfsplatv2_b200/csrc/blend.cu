@@ -25,7 +25,7 @@
 
 namespace spf {
 
-constexpr int CH_F = 128;  // records per forward chunk  (6 KB slab + 2 KB boxes)
+constexpr int CH_F = 256;  // records per forward chunk  (12 KB slab + 4 KB boxes)
 constexpr int CH_B = 64;   // records per backward chunk
 
 __device__ __forceinline__ void warp_block_of_thread(int tid, int tile, int gx, int& bx, int& by) {
@@ -115,6 +115,10 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   bool done = !inside;
   int pending = -1;  // chunk whose TMA load is in flight beyond the current one
 
+  // Lists of at most two chunks (the common case) live entirely in the two buffers: nothing is ever refilled, so the
+  // warps need no block barrier at all -- each waits on the chunk's mbarrier and leaves as soon as ITS 32 pixels are
+  // done.  Longer lists recycle the buffers and keep the block in step.
+  const bool free_running = TMA && (nchunks <= 2);
   if (nchunks > 0) stage_chunk<TMA>(buf[0], box[0], slab, cull, min(CH_F, L), &bar[0], tid);
   for (int c = 0; c < nchunks; ++c) {
     const int cnt = min(CH_F, L - c * CH_F);
@@ -178,7 +182,11 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
         }
       }
     }
-    if (__syncthreads_and(done)) break;
+    if (free_running) {
+      if (__all_sync(0xffffffffu, done)) break;
+    } else if (__syncthreads_and(done)) {
+      break;
+    }
   }
   if (TMA && pending >= 0 && tid == 0) mbar_wait(&bar[pending & 1], (uint32_t)((pending >> 1) & 1));
   if (LOG) {
