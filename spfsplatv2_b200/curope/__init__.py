@@ -79,3 +79,24 @@ class cuRoPE2D(torch.nn.Module):
     def forward(self, tokens, positions):
         cuRoPE2D_func.apply(tokens.transpose(1, 2), positions, self.base, self.F0)
         return tokens
+
+
+class RotaryPositionEmbedding2D(torch.nn.Module):
+    """Drop-in for the VGGT backbone's pure-PyTorch 2-D RoPE
+    (/root/reference/src/model/encoder/backbone/vggt/layers/rope.py:62-188): same math as ``cuRoPE2D`` but OUT of place,
+    ``tokens`` [B, H, N, D] -> new tensor.  Runs on the same sm_100a kernel (no cos/sin tables, no
+    ``int(positions.max())`` host sync); ``scaling_factor`` is accepted and, as in the reference, unused."""
+
+    def __init__(self, frequency: float = 100.0, scaling_factor: float = 1.0):
+        super().__init__()
+        self.base_frequency = frequency
+        self.scaling_factor = scaling_factor
+
+    def forward(self, tokens: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        assert tokens.size(-1) % 2 == 0, "Feature dimension must be even"
+        assert positions.ndim == 3 and positions.shape[-1] == 2, "Positions must have shape (batch_size, n_tokens, 2)"
+        work = tokens.transpose(1, 2).contiguous()               # [B, N, H, D] private copy (the op is out of place)
+        if work.data_ptr() == tokens.data_ptr():
+            work = work.clone()
+        work = cuRoPE2D_func.apply(work, positions.contiguous(), float(self.base_frequency), 1.0)
+        return work.transpose(1, 2)

@@ -172,3 +172,22 @@ def test_fused_image_losses_match_reference_definitions():
     a = mse_loss(pred.detach(), gt)
     b = mse_loss(pred.detach(), gt)
     assert torch.equal(a, b)                                               # deterministic
+
+
+def test_vggt_rope_module_matches_reference_pytorch_rope(rope_gold):
+    """RotaryPositionEmbedding2D (VGGT backbone, vggt/layers/rope.py:62-188 -- the same function as the CroCo RoPE2D whose
+    outputs are in the golden file): out of place, [B,H,N,D] layout, differentiable."""
+    from spfsplatv2_b200.curope import RotaryPositionEmbedding2D
+    tok = torch.from_numpy(rope_gold["vit_tokens"]).to(D0)           # [B,N,H,D]
+    pos = torch.from_numpy(rope_gold["vit_pos"]).to(D0)
+    x = tok.transpose(1, 2).contiguous().requires_grad_()            # [B,H,N,D] as the attention layers pass it
+    rope = RotaryPositionEmbedding2D(frequency=float(rope_gold["vit_base"]))
+    y = rope(x, pos)
+    assert y.shape == x.shape and y.data_ptr() != x.data_ptr()
+    assert torch.equal(x.detach(), tok.transpose(1, 2))              # input untouched
+    want = torch.from_numpy(rope_gold["vit_pytorch_fwd"]).to(D0).transpose(1, 2)
+    assert (y - want).abs().max().item() < 2e-5
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    gwant = RO.rope_2d(w.transpose(1, 2).contiguous().cpu().numpy(), rope_gold["vit_pos"], float(rope_gold["vit_base"]), -1.0)
+    assert (x.grad.transpose(1, 2).cpu() - torch.from_numpy(gwant)).abs().max().item() < 2e-5
