@@ -47,8 +47,10 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """Samples nvidia-smi clocks / throttle reasons (every 20 ms, with timestamps) while the GPU is under load; stop()
+    reports the samples that fall inside the timed region, or -- if the timed region was shorter than the sampling
+    period allows -- those taken over the whole loaded span (warm-up + timed + end-to-end loops), and says which."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -56,11 +58,12 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.window = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -68,7 +71,10 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark(self, t0: float, t1: float):
+        self.window = (t0, t1)
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -78,21 +84,29 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+
+        def parse(lines):
+            sm, mx, reasons = [], None, set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2])); mx = float(f[3])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            sm.sort()
+            return sm, mx, reasons
+        inside = [x for x in self.lines if self.window and self.window[0] <= x[0] <= self.window[1] + 0.02]
+        span = "timed region"
+        if len(inside) < 2:
+            inside, span = self.lines[1:] if len(self.lines) > 1 else self.lines, "warm-up + timed + end-to-end loops (timed region shorter than 2 samples)"
+        sm, mx, reasons = parse(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": span}
 
 
 def _make_inputs(workload: str, rank: int, pin: bool):
@@ -245,9 +259,12 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_mark0 = time.time()
     ms, wall = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.mark(time.time() - wall / 1e3, time.time())
     ms_e2e, wall_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    clocks = sampler.stop() if rank == 0 else None
 
     views_total = b * world
     value = views_total * args.steps / (ms / 1e3)
