@@ -1,22 +1,25 @@
-// K6 / K7: per-16x16-tile front-to-back alpha blend (forward) and its backward.
+// K5 / K6: per-16x16-tile front-to-back alpha blend (forward) and its backward(s).
 //
-// One CTA (256 threads, one pixel each; every warp owns an 8x4 pixel block) per (view, tile).  The
-// tile's depth-sorted slab -- contiguous 48-byte records {xy, conic, opacity, rgb, depth, slot, id} --
-// and the matching 16-byte alpha bounding boxes are streamed through a double-buffered
-// shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx).
+// One CTA (256 threads, one pixel each; every warp owns an 8x4 pixel block) per (view, tile).  The tile's
+// depth-sorted slab -- contiguous 48-byte records {xy, conic, opacity, rgb, depth, slot, id} -- and the matching
+// 16-byte alpha bounding boxes are streamed through a double-buffered shared-memory ring with 1-D TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx).
 //
-// Culling: with the encoder's scale law most splats are ~2 px wide, so >90% of (pixel, Gaussian)
-// pairs of a tile are rejections.  Each warp therefore first tests 32 records at a time, one record
-// per LANE, against its 8x4 pixel block (box vs box, conflict-free LDS.128), ballots, and then walks
-// only the set bits with all 32 lanes evaluating their own pixel.  The boxes are conservative
-// (binning.cu: alpha_bbox), the per-pixel test is unchanged, so results are bit-identical to the
-// unculled loop.
+// Culling: with the encoder's scale law most splats are ~2 px wide, so >90% of (pixel, Gaussian) pairs of a tile
+// are rejections.  Each warp therefore first tests 32 records at a time, one record per LANE, against its 8x4
+// pixel block (box vs box, conflict-free LDS.128), ballots, and then walks only the set bits with all 32 lanes
+// evaluating their own pixel.  The boxes are conservative (binning.cu: alpha_bbox), the per-pixel test is
+// unchanged, so results are bit-identical to the unculled loop.
 //
-// Backward walks the list back to front (per pixel from its own n_contrib).  Per-Gaussian partial
-// gradients (10 floats) are reduced across the warp with a 12-shuffle recursive-halving butterfly
-// (skipped when no lane touches the Gaussian), across the 8 warps through shared memory in a fixed
-// order, and written with ONE plain store per (Gaussian, tile) duplicate into that duplicate's
-// private slot: no atomics anywhere, bit-reproducible.
+// Backward, three generations (all atomic-free on floats, fixed summation order => bit-reproducible):
+//   blend_backward_log_kernel  (default)  consumes the PAIR LOG the forward writes when a backward will follow:
+//                              one contributing (pixel, Gaussian) pair per lane, closed-form dL/dalpha, segmented
+//                              shuffle reduction per Gaussian, exchange slots for Gaussians overlapping several
+//                              warp regions.
+//   blend_backward_kernel      recomputing pair-compaction kernel: per-tile fallback when a warp's log overflowed,
+//                              and the backward when no log was requested.
+//   blend_backward_v1_kernel   first generation (back to front, 12-shuffle butterfly per hit), SPF_FLAG_BWD_V1,
+//                              kept as an independent cross-check.
 //
 // Replaces renderCUDA forward/backward of diff_gauss_pose (SURVEY.md App. B "Blend forward/backward").
 #include "spf_device.cuh"
