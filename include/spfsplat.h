@@ -202,6 +202,15 @@ SPF_API int spf_image_mse_blocks(int64_t n_per_image);
 SPF_API int spf_image_mse(const float* pred, const float* target, int32_t n_images, int64_t n_per_image, int32_t clip,
                   float grad_scale, float* dL_dpred, float* partial, float* mse_per_image, float* mean_all, void* stream);
 
+/* Fused UnifiedGaussianAdapter (src/model/encoder/common/gaussian_adapter.py:122-150): raw [n, 7 + 3*sh_coeffs] ->
+ * scales [n,3] = min(0.3, 0.001 softplus), rotations [n,4] = q / (|q| + eps), harmonics [n,3,sh_coeffs] = raw * sh_mask
+ * (sh_mask per degree as gaussian_adapter.py:42-48).  The [n,3,3] covariances the reference also builds are never read
+ * by the decoder and are not produced.  Backward: any of the three upstream gradients may be NULL (= zero). */
+SPF_API int spf_adapter_forward(const float* raw, int64_t n, int32_t sh_coeffs, float eps, float* scales, float* rotations,
+                        float* harmonics, void* stream);
+SPF_API int spf_adapter_backward(const float* raw, const float* dL_dscales, const float* dL_drotations,
+                         const float* dL_dharmonics, int64_t n, int32_t sh_coeffs, float eps, float* dL_draw, void* stream);
+
 /* 2-D RoPE, in place.  Replaces rope_2d (curope.cpp:49-65).  tokens: [B,N,H,D] view with
  * stride(3)==1, stride(2)==D (kernels.cu:91); positions int64 [B,N,2] contiguous.
  * dtype: 0 = fp32, 1 = fp16, 2 = bf16.  fwd = +F0 forward, -F0 backward. */

@@ -1,0 +1,116 @@
+// Fused UnifiedGaussianAdapter: raw head output [N, 7 + 3K] -> scales [N,3], rotations [N,4],
+// harmonics [N,3,K] in ONE pass (and its backward), without materialising the [N,3,3] covariances the decoder never
+// reads.  Replaces the ~10 elementwise torch kernels of
+//   UnifiedGaussianAdapter.forward   /root/reference/src/model/encoder/common/gaussian_adapter.py:122-150
+//     scales    = clamp_max(0.001 * softplus(raw[0:3]), 0.3)
+//     rotations = raw[3:7] / (|raw[3:7]| + eps)
+//     harmonics = raw[7:].view(3, K) * sh_mask          (sh_mask[0] = 1, degree d >= 1: 0.1 * 0.25^d, :42-48)
+// HBM-bound: 2 * (7 + 3K) * 4 bytes per Gaussian each way.  A block stages 128 raw rows in shared memory with coalesced
+// 128-bit loads and writes the three outputs element-parallel (coalesced) -- no per-thread 328-byte strides.
+#include "spf_device.cuh"
+#include "spf_kernels.h"
+
+namespace spf {
+
+constexpr int AD_ROWS = 128;
+constexpr int AD_THREADS = 256;
+
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.0f ? x : log1pf(expf(x)); }   // torch: beta 1, threshold 20
+__device__ __forceinline__ float sh_mask_of(int k) {
+  const int deg = (k >= 16) ? 4 : (k >= 9) ? 3 : (k >= 4) ? 2 : (k >= 1) ? 1 : 0;
+  const float m[5] = {1.0f, 0.1f * 0.25f, 0.1f * 0.0625f, 0.1f * 0.015625f, 0.1f * 0.00390625f};
+  return m[deg];
+}
+
+__global__ void __launch_bounds__(AD_THREADS)
+adapter_forward_kernel(const float* __restrict__ raw, int64_t n, int K, float eps, float* __restrict__ scales,
+                       float* __restrict__ rots, float* __restrict__ sh) {
+  extern __shared__ __align__(16) float tile[];
+  const int R = 7 + 3 * K;
+  const int64_t g0 = (int64_t)blockIdx.x * AD_ROWS;
+  const int rows = (int)min((int64_t)AD_ROWS, n - g0);
+  block_copy_g2s(tile, raw + g0 * R, rows * R, R, R, threadIdx.x, AD_THREADS);
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows * 3; i += AD_THREADS) {
+    const int g = i / 3, c = i - g * 3;
+    scales[g0 * 3 + i] = fminf(0.001f * softplus_t(tile[g * R + c]), 0.3f);
+  }
+  for (int i = threadIdx.x; i < rows * 4; i += AD_THREADS) {
+    const int g = i >> 2, c = i & 3;
+    const float* q = tile + g * R + 3;
+    const float nrm = sqrtf((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
+    rots[g0 * 4 + i] = q[c] / (nrm + eps);
+  }
+  const int W = 3 * K;
+  for (int i = threadIdx.x; i < rows * W; i += AD_THREADS) {
+    const int g = i / W, j = i - g * W;
+    sh[g0 * W + i] = tile[g * R + 7 + j] * sh_mask_of(j % K);
+  }
+}
+
+__global__ void __launch_bounds__(AD_THREADS)
+adapter_backward_kernel(const float* __restrict__ raw, const float* __restrict__ d_scales, const float* __restrict__ d_rots,
+                        const float* __restrict__ d_sh, int64_t n, int K, float eps, float* __restrict__ d_raw) {
+  extern __shared__ __align__(16) float tile[];      // raw rows, overwritten in place by d_raw rows
+  __shared__ float dq[AD_ROWS * 4];
+  const int R = 7 + 3 * K;
+  const int64_t g0 = (int64_t)blockIdx.x * AD_ROWS;
+  const int rows = (int)min((int64_t)AD_ROWS, n - g0);
+  block_copy_g2s(tile, raw + g0 * R, rows * R, R, R, threadIdx.x, AD_THREADS);
+  for (int i = threadIdx.x; i < rows * 4; i += AD_THREADS) dq[i] = d_rots ? d_rots[g0 * 4 + i] : 0.0f;
+  __syncthreads();
+  // quaternion part first (needs all four raw components of a row before any is overwritten): one thread per row
+  for (int g = threadIdx.x; g < rows; g += AD_THREADS) {
+    float* q = tile + g * R + 3;
+    const float q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    const float nrm = sqrtf((q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3));
+    const float inv = 1.0f / (nrm + eps);
+    const float dot = (q0 * dq[g * 4] + q1 * dq[g * 4 + 1]) + (q2 * dq[g * 4 + 2] + q3 * dq[g * 4 + 3]);
+    // d/dq_raw [ q / (|q| + eps) ] = dq/(n+eps) - q (q . dq) / (n (n+eps)^2)
+    const float k = (nrm > 0.0f) ? dot * inv * inv / nrm : 0.0f;
+    q[0] = dq[g * 4] * inv - q0 * k; q[1] = dq[g * 4 + 1] * inv - q1 * k;
+    q[2] = dq[g * 4 + 2] * inv - q2 * k; q[3] = dq[g * 4 + 3] * inv - q3 * k;
+  }
+  for (int i = threadIdx.x; i < rows * 3; i += AD_THREADS) {
+    const int g = i / 3, c = i - g * 3;
+    const float x = tile[g * R + c];
+    const float sp = 0.001f * softplus_t(x);
+    const float sig = 1.0f / (1.0f + expf(-x));
+    const float gs = d_scales ? d_scales[g0 * 3 + i] : 0.0f;
+    tile[g * R + c] = (sp < 0.3f || sp == 0.3f) ? gs * 0.001f * ((x > 20.0f) ? 1.0f : sig) : 0.0f;   // clamp_max passes at equality
+  }
+  const int W = 3 * K;
+  for (int i = threadIdx.x; i < rows * W; i += AD_THREADS) {
+    const int g = i / W, j = i - g * W;
+    tile[g * R + 7 + j] = d_sh ? d_sh[g0 * W + i] * sh_mask_of(j % K) : 0.0f;
+  }
+  __syncthreads();
+  block_copy_s2g(d_raw + g0 * R, tile, rows * R, R, R, threadIdx.x, AD_THREADS);
+}
+
+cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, float* scales, float* rots, float* sh,
+                                   cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const size_t smem = (size_t)AD_ROWS * (7 + 3 * K) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(adapter_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  adapter_forward_kernel<<<(unsigned)((n + AD_ROWS - 1) / AD_ROWS), AD_THREADS, smem, s>>>(raw, n, K, eps, scales, rots, sh);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adapter_backward(const float* raw, const float* d_scales, const float* d_rots, const float* d_sh,
+                                    int64_t n, int K, float eps, float* d_raw, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const size_t smem = (size_t)AD_ROWS * (7 + 3 * K) * sizeof(float);
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(adapter_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  adapter_backward_kernel<<<(unsigned)((n + AD_ROWS - 1) / AD_ROWS), AD_THREADS, smem, s>>>(raw, d_scales, d_rots, d_sh, n, K,
+                                                                                          eps, d_raw);
+  return cudaGetLastError();
+}
+
+}  // namespace spf

@@ -213,6 +213,26 @@ int spf_image_mse(const float* pred, const float* target, int32_t n_images, int6
   return SPF_OK;
 }
 
+int spf_adapter_forward(const float* raw, int64_t n, int32_t sh_coeffs, float eps, float* scales, float* rotations,
+                        float* harmonics, void* stream) {
+  if (!raw || !scales || !rotations || !harmonics) return fail(SPF_ERR_BAD_ARG, "spf_adapter_forward: NULL pointer");
+  if (n < 0 || sh_coeffs < 1 || sh_coeffs > spf::MAX_SH_COEFFS) return fail(SPF_ERR_BAD_ARG, "spf_adapter_forward: bad sizes");
+  cudaError_t e = spf::launch_adapter_forward(raw, n, sh_coeffs, eps, scales, rotations, harmonics,
+                                              static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_forward");
+  return SPF_OK;
+}
+
+int spf_adapter_backward(const float* raw, const float* dL_dscales, const float* dL_drotations, const float* dL_dharmonics,
+                         int64_t n, int32_t sh_coeffs, float eps, float* dL_draw, void* stream) {
+  if (!raw || !dL_draw) return fail(SPF_ERR_BAD_ARG, "spf_adapter_backward: NULL pointer");
+  if (n < 0 || sh_coeffs < 1 || sh_coeffs > spf::MAX_SH_COEFFS) return fail(SPF_ERR_BAD_ARG, "spf_adapter_backward: bad sizes");
+  cudaError_t e = spf::launch_adapter_backward(raw, dL_dscales, dL_drotations, dL_dharmonics, n, sh_coeffs, eps, dL_draw,
+                                               static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_backward");
+  return SPF_OK;
+}
+
 int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
                int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
   if (!tokens || !positions) return fail(SPF_ERR_BAD_ARG, "tokens / positions are NULL");

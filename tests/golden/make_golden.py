@@ -8,6 +8,7 @@ Fixtures
   rope_ref.npz      outputs of the reference's rope_2d_cpu (curope.cpp:11-47, compiled unmodified into
                     oracle/_ref/curope_ref*.so) and of its pure-PyTorch RoPE2D fallback (pos_embed.py:112-159)
                     on seeded tokens / positions, forward (+F0) and backward (-F0).
+  adapter_ref.npz   the reference's UnifiedGaussianAdapter (gaussian_adapter.py:122-150): outputs and d/d(raw) of a seeded loss.
   ortho_ref.npz     the reference's render_cuda_orthographic (cuda_splatting.py:146-255) on a seeded box of Gaussians, same
                     recording stand-in for the rasterizer: image + the arguments it passes (tensor-valued tanfov).
   decoder_ref.npz   the reference's UNMODIFIED DecoderSplattingCUDA.forward (decoder_splatting_cuda.py:41-78) and
@@ -93,7 +94,8 @@ def _stub_modules():
                  "lightning.pytorch.loggers.wandb", "lightning.pytorch.utilities", "lightning.pytorch.callbacks",
                  "lightning.pytorch.plugins.environments", "lightning.pytorch.plugins", "matplotlib.pyplot",
                  "matplotlib.cm", "matplotlib.colors", "lpips", "plyfile", "wandb", "colorspacious", "moviepy",
-                 "moviepy.editor", "hydra", "skimage", "skimage.metrics", "roma", "e3nn", "timm"):
+                 "moviepy.editor", "hydra", "skimage", "skimage.metrics", "roma", "e3nn", "e3nn.o3", "timm", "timm.models",
+                 "timm.models.layers", "timm.layers", "huggingface_hub", "safetensors", "safetensors.torch", "xformers", "xformers.ops"):
         if name not in sys.modules:
             try:
                 __import__(name)
@@ -240,12 +242,39 @@ def make_orthographic():
     print(f"orthographic: image mean {img.mean().item():.4f}, tanfov types {r['tanfov_types']}, covered {(img[0] != bg.view(3,1,1)).any(0).float().mean():.2f}")
 
 
+def make_adapter():
+    """The reference's UnifiedGaussianAdapter (gaussian_adapter.py:122-150), forward and backward, on seeded raw head
+    outputs incl. scale logits beyond the softplus threshold (20) and the 0.3 clamp."""
+    _stub_modules()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from src.model.encoder.common.gaussian_adapter import GaussianAdapterCfg, UnifiedGaussianAdapter
+    ad = UnifiedGaussianAdapter(GaussianAdapterCfg(gaussian_scale_min=0.5, gaussian_scale_max=15.0, sh_degree=4))
+    g = torch.Generator().manual_seed(11)
+    b, n = 2, 301
+    raw = torch.randn(b, n, 82, generator=g)
+    raw[0, :8, 0] = torch.tensor([25.0, 19.9, 20.1, -30.0, 350.0, 299.9, 300.5, 0.0])     # softplus threshold / 0.3 clamp
+    raw[1, 0, 3:7] = 0.0                                                               # zero quaternion (eps path)
+    raw = raw.requires_grad_()
+    means = torch.randn(b, n, 3, generator=g)
+    opac = torch.rand(b, n, generator=g)
+    out = ad.forward(means, opac, raw)
+    ws, wr, wh = torch.randn(b, n, 3, generator=g), torch.randn(b, n, 4, generator=g), torch.randn(b, n, 3, 25, generator=g)
+    ((out.scales * ws).sum() + (out.rotations * wr).sum() + (out.harmonics * wh).sum()).backward()
+    np.savez_compressed(os.path.join(HERE, "adapter_ref.npz"), raw=raw.detach().numpy(), means=means.numpy(), opacities=opac.numpy(),
+                        scales=out.scales.detach().numpy(), rotations=out.rotations.detach().numpy(),
+                        harmonics=out.harmonics.detach().numpy(), ws=ws.numpy(), wr=wr.numpy(), wh=wh.numpy(),
+                        d_raw=raw.grad.numpy(), sh_mask=ad.sh_mask.numpy())
+    print(f"adapter: scales max {out.scales.max().item():.3f}, d_raw norm {raw.grad.norm().item():.3f}")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("make_golden.py needs /root/reference (run it in the build container)")
     make_rope()
     make_decoder()
     make_orthographic()
+    make_adapter()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -191,3 +191,35 @@ def test_vggt_rope_module_matches_reference_pytorch_rope(rope_gold):
     (y * w).sum().backward()
     gwant = RO.rope_2d(w.transpose(1, 2).contiguous().cpu().numpy(), rope_gold["vit_pos"], float(rope_gold["vit_base"]), -1.0)
     assert (x.grad.transpose(1, 2).cpu() - torch.from_numpy(gwant)).abs().max().item() < 2e-5
+
+
+def test_fused_adapter_matches_reference_adapter_golden():
+    """spfsplatv2_b200.adapter.UnifiedGaussianAdapter vs the reference's (gaussian_adapter.py:122-150) outputs and d/d(raw),
+    incl. the softplus threshold, the 0.3 clamp and a zero quaternion (eps path)."""
+    from spfsplatv2_b200.adapter import GaussianAdapterCfg, UnifiedGaussianAdapter
+    g = np.load(os.path.join(GOLD, "adapter_ref.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(D0)
+    ad = UnifiedGaussianAdapter(GaussianAdapterCfg(0.5, 15.0, 4))
+    raw = t("raw").requires_grad_()
+    out = ad(t("means"), t("opacities"), raw)
+    assert out.covariances.shape == (*g["opacities"].shape, 3, 3) and out.harmonics.shape == g["harmonics"].shape
+    assert torch.allclose(out.scales, t("scales"), rtol=2e-6, atol=1e-9)
+    assert torch.allclose(out.rotations, t("rotations"), rtol=2e-6, atol=1e-7)
+    assert torch.equal(out.harmonics, t("harmonics"))
+    assert torch.equal(out.means, t("means")) and torch.equal(out.opacities, t("opacities"))
+    ((out.scales * t("ws")).sum() + (out.rotations * t("wr")).sum() + (out.harmonics * t("wh")).sum()).backward()
+    want = t("d_raw")
+    assert torch.allclose(raw.grad[..., :3], want[..., :3], rtol=1e-5, atol=1e-9)             # scales (softplus, clamp)
+    assert torch.allclose(raw.grad[..., 3:7], want[..., 3:7], rtol=2e-5, atol=2e-6)          # quaternion (cancellation)
+    assert torch.allclose(raw.grad[..., 7:], want[..., 7:], rtol=1e-6, atol=0)                # SH mask
+    # a decoder call on the adapter's output works end to end (stride-0 covariances, expanded views)
+    from spfsplatv2_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg
+    dec = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], True, True, True)).to(D0)
+    b, n = g["opacities"].shape
+    means = t("means") * 0.3 + torch.tensor([0.0, 0.0, 4.0], device=D0)
+    gs = ad(means, t("opacities"), raw.detach().clone().requires_grad_())
+    ext = torch.eye(4, device=D0).repeat(b, 1, 1, 1)
+    K = torch.tensor([[0.88, 0, 0.5], [0, 0.88, 0.5], [0, 0, 1.0]], device=D0).repeat(b, 1, 1, 1)
+    o = dec(gs, ext, K, torch.full((b, 1), 0.5, device=D0), torch.full((b, 1), 100.0, device=D0), (32, 32))
+    o.color.mean().backward()
+    assert torch.isfinite(o.color).all()
