@@ -9,7 +9,6 @@ namespace spf {
 
 constexpr int PROJ_THREADS = 128;   // Gaussians per projection block
 constexpr int TILE_THREADS = 256;   // 16x16 pixels
-constexpr int SORT_SMEM_CAP = 4096; // per-tile list length sorted in shared memory
 
 // control buffer layout (int32 words)
 struct ControlLayout {

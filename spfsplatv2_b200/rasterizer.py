@@ -45,9 +45,6 @@ def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _raw_stream(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
-
 
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
