@@ -84,3 +84,39 @@ def test_no_product_import_of_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+
+
+def test_install_shims_registers_the_modules_the_reference_imports():
+    """`import diff_gauss_pose` (cuda_splatting.py:5) and `import curope` (curope2d.py:6-9) resolve to the drop-ins, with the
+    reference's names; the product path refuses CPU tensors instead of falling back."""
+    import importlib
+    import sys
+
+    import torch
+
+    import spfsplatv2_b200
+    saved = {k: sys.modules.get(k) for k in ("diff_gauss_pose", "curope")}
+    try:
+        spfsplatv2_b200.install_shims()
+        dgp = importlib.import_module("diff_gauss_pose")
+        cur = importlib.import_module("curope")
+        assert dgp.GaussianRasterizationSettings._fields == (
+            "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "projmatrix", "sh_degree",
+            "prefiltered", "debug", "enable_cov_grad", "enable_sh_grad")
+        assert callable(cur.rope_2d) and hasattr(cur, "cuRoPE2D") and hasattr(cur, "cuRoPE2D_func")
+        with pytest.raises(RuntimeError, match="CUDA tensors"):
+            cur.rope_2d(torch.zeros(1, 2, 1, 8), torch.zeros(1, 2, 2, dtype=torch.int64), 100.0, 1.0)
+        s = dgp.GaussianRasterizationSettings(8, 8, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), 0, False, False)
+        with pytest.raises(RuntimeError, match="CUDA tensors"):
+            dgp.GaussianRasterizer(s)(means3D=torch.zeros(2, 3), means2D=None, opacities=torch.ones(2, 1),
+                                      colors_precomp=torch.ones(2, 3), scales=torch.ones(2, 3),
+                                      rotations=torch.tensor([[1.0, 0, 0, 0]] * 2), viewmatrix=torch.eye(4))
+        with pytest.raises(Exception, match="SHs or precomputed colors"):
+            dgp.GaussianRasterizer(s)(means3D=torch.zeros(2, 3), means2D=None, opacities=torch.ones(2, 1),
+                                      scales=torch.ones(2, 3), rotations=torch.ones(2, 4), viewmatrix=torch.eye(4))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
