@@ -1,0 +1,1 @@
+"""Test infrastructure only: CPU oracles (never imported by the product path)."""
