@@ -272,11 +272,19 @@ tile_sort_pack_kernel(Dims d, SpfRasterState st, const int* __restrict__ tile_st
     pack_records(d, st, gk, n, s64, view, tile, tid);
     return;
   }
-  // 1. min / max of the depth bits (keys stay in global memory / L2 until the scatter)
+  // 1. the keys are read from global memory ONCE into registers (KPT per thread) and reused by the min/max pass,
+  //    the histogram and the scatter: every extra pass would be another dependent trip to L2 per block
+  constexpr int KPT = CAP / TILE_THREADS;
+  uint64_t kreg[KPT];
   unsigned mn = 0xffffffffu, mx = 0u;
-  for (int i = tid; i < n; i += TILE_THREADS) {
-    const unsigned hi = (unsigned)(gk[i] >> 32);
-    mn = min(mn, hi); mx = max(mx, hi);
+#pragma unroll
+  for (int q = 0; q < KPT; ++q) {
+    const int i = tid + q * TILE_THREADS;
+    kreg[q] = (i < n) ? gk[i] : ~0ull;
+    if (i < n) {
+      const unsigned hi = (unsigned)(kreg[q] >> 32);
+      mn = min(mn, hi); mx = max(mx, hi);
+    }
   }
   for (int i = tid; i < NBK; i += TILE_THREADS) S.cur[i] = 0;
   if (tid == 0) S.bad = 0;
@@ -295,7 +303,9 @@ tile_sort_pack_kernel(Dims d, SpfRasterState st, const int* __restrict__ tile_st
     return min(b, NBK - 1);
   };
   // 2. histogram
-  for (int i = tid; i < n; i += TILE_THREADS) atomicAdd(&S.cur[bucket_of(gk[i])], 1);
+#pragma unroll
+  for (int q = 0; q < KPT; ++q)
+    if (tid + q * TILE_THREADS < n) atomicAdd(&S.cur[bucket_of(kreg[q])], 1);
   __syncthreads();
   // 3. exclusive scan of the NBK counters, in place: cur[b] = first slot of bucket b
   {
@@ -315,17 +325,18 @@ tile_sort_pack_kernel(Dims d, SpfRasterState st, const int* __restrict__ tile_st
   }
   __syncthreads();
   if (S.bad) {                             // degenerate depth distribution: bitonic network
-    for (int i = tid; i < n; i += TILE_THREADS) S.b[i] = gk[i];
+#pragma unroll
+    for (int q = 0; q < KPT; ++q)
+      if (tid + q * TILE_THREADS < n) S.b[tid + q * TILE_THREADS] = kreg[q];
     __syncthreads();
     bitonic_sort(S.b, n, tid, TILE_THREADS);
     pack_records(d, st, S.b, n, s64, view, tile, tid);
     return;
   }
   // 4. scatter into bucket order (arbitrary order inside a bucket); afterwards cur[b] = END of bucket b
-  for (int i = tid; i < n; i += TILE_THREADS) {
-    const uint64_t k = gk[i];
-    S.b[atomicAdd(&S.cur[bucket_of(k)], 1)] = k;
-  }
+#pragma unroll
+  for (int q = 0; q < KPT; ++q)
+    if (tid + q * TILE_THREADS < n) S.b[atomicAdd(&S.cur[bucket_of(kreg[q])], 1)] = kreg[q];
   __syncthreads();
   // 5. exact rank inside the bucket by full-key comparison (keys are unique: a Gaussian occurs once per tile);
   //    the sorted list goes back to the (fully consumed) global bucket, where the pack step streams it from
