@@ -159,8 +159,13 @@ def run_ours(args):
     # stand-in for the replicated-parameter gradient all-reduce of the DDP training step: one 64 MiB
     # bucket per step, launched on a side stream behind the backward, joined before the next step's timing point
     from spfsplatv2_b200.dp import GradAllReduce
-    ar_buf = torch.zeros(16 * 1024 * 1024, device=dev) if world > 1 else None
+    # On NVSwitch boxes the bucket is symmetric memory reduced in the switch by csrc/allreduce.cu (NVLS multimem);
+    # elsewhere (or with SPF_ALLREDUCE=nccl) it is a plain tensor reduced by NCCL.
     reducer = GradAllReduce(dev) if world > 1 else None
+    ar_buf = reducer.alloc(16 * 1024 * 1024) if world > 1 else None
+    ar_backend = ("nvls" if reducer.uses_nvls(ar_buf) else "nccl") if world > 1 else None
+    if world > 1 and rank == 0 and reducer.nvls_error:
+        print(f"bench.py: NVLS all-reduce unavailable ({reducer.nvls_error}); using NCCL", file=sys.stderr)
 
     def step_resident():
         loss, leaves, ext = _step(dec, Gaussians, dev_in)
@@ -308,13 +313,13 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "views_per_step_per_gpu": b, "gaussians_per_scene": P,
                        "duplicates_per_step": N, "image": [h, w], "sh_degree": 4,
-                       "parallelism": f"dp{world} (scenes sharded over ranks; 64 MiB stand-in grad all-reduce/step)" if world > 1 else "single GPU",
+                       "parallelism": f"dp{world} (scenes sharded over ranks; 64 MiB stand-in grad all-reduce/step, {ar_backend})" if world > 1 else "single GPU",
                        "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step > 126 MB L2, no explicit flush",
                        "loop": "one CUDA graph per step (fwd + fused MSE + bwd)" if graphed else "eager PyTorch loop",
                        "loss": "fused MSE (spfsplatv2_b200.loss.mse_loss)"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(max(ms_e2e, wall_e2e) / args.steps, 4)},
-            "gpu_launches": 13 * args.steps,   # camera fwd/bwd, project fwd/bwd, scan, emit, sort+pack, blend fwd, blend bwd (log + fallback), pose reduce, fused MSE loss (2)
+            "gpu_launches": (13 + (1 if ar_backend == "nvls" else 0)) * args.steps,   # (+ the multimem all-reduce kernel at N>1) camera fwd/bwd, project fwd/bwd, scan, emit, sort+pack, blend fwd, blend bwd (log + fallback), pose reduce, fused MSE loss (2)
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),

@@ -233,6 +233,19 @@ int spf_adapter_backward(const float* raw, const float* dL_dscales, const float*
   return SPF_OK;
 }
 
+int spf_multimem_allreduce_f32(float* multicast_bucket, int64_t numel, int32_t rank, int32_t world, int32_t n_blocks,
+                               void* stream) {
+  if (!multicast_bucket) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: multicast address is NULL");
+  if ((reinterpret_cast<uintptr_t>(multicast_bucket) & 15) != 0 || numel < 0 || (numel & 3) != 0)
+    return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: bucket must be 16-byte aligned with numel % 4 == 0");
+  if (world < 1 || rank < 0 || rank >= world) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: bad rank / world");
+  if (n_blocks < 1 || n_blocks > 148) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: n_blocks must be 1..148");
+  cudaError_t e = spf::launch_multimem_allreduce_f32(multicast_bucket, numel, rank, world, n_blocks,
+                                                     static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "multimem_allreduce_f32");
+  return SPF_OK;
+}
+
 int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
                int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
   if (!tokens || !positions) return fail(SPF_ERR_BAD_ARG, "tokens / positions are NULL");

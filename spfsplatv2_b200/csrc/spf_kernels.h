@@ -63,6 +63,7 @@ cudaError_t launch_camera_backward(int B, int scale_invariant, const float* near
 cudaError_t launch_image_mse(const float* pred, const float* target, int n_images, int64_t n_per_image, int clip,
                              float grad_scale, float* dL_dpred, float* partial, int blocks_per_image,
                              float* mse_per_image, float* mean_all, cudaStream_t s);
+cudaError_t launch_multimem_allreduce_f32(float* mc, int64_t numel, int rank, int world, int n_blocks, cudaStream_t s);
 cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, float* scales, float* rots, float* sh,
                                    cudaStream_t s);
 cudaError_t launch_adapter_backward(const float* raw, const float* d_scales, const float* d_rots, const float* d_sh,

@@ -13,10 +13,15 @@ data-path collective; the only exchange is the gradient of whatever is REPLICATE
     replicated, the views are sharded -> the Gaussian-parameter gradients are summed over ranks, the per-view
     pose gradients stay rank-local.
 
-Backend-agnostic (`nccl` on the GPUs, `gloo` in the CPU tests); no renderer code in here.
+Backend-agnostic (`nccl` on the GPUs, `gloo` in the CPU tests); no renderer code in here.  On NVSwitch machines a
+bucket allocated with `GradAllReduce.alloc()` lives in symmetric memory and is reduced INSIDE the switch by this
+repo's own multimem kernel (csrc/allreduce.cu, C entry `spf_multimem_allreduce_f32`) instead of NCCL; torch's
+symmetric-memory module only provides the allocation, the multicast binding and the cross-rank barrier.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -39,13 +44,89 @@ class GradAllReduce:
     On CUDA the bucket copy + collective run on `self.stream` after an event recorded on the producer's stream,
     so they overlap whatever the caller enqueues next (the next step's forward).  On CPU (gloo) it is synchronous."""
 
-    def __init__(self, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, device: torch.device, group: Optional[dist.ProcessGroup] = None, backend: str = "auto",
+                 nvls_blocks: Optional[int] = None):
+        """backend: "nccl" = torch.distributed only; "nvls" = in-switch multimem kernel for buckets from `alloc()`
+        (raises if the machine has no multicast support); "auto" = nvls when available, else nccl.  Overridable
+        with SPF_ALLREDUCE=nccl|nvls|auto; SPF_NVLS_BLOCKS sets the CTAs the multimem kernel may occupy."""
         self.device = torch.device(device)
         self.group = group
         self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._bucket: Optional[Tensor] = None
         self._views: List[Tensor] = []
         self._targets: List[Tensor] = []
+        self.backend = os.environ.get("SPF_ALLREDUCE", backend)
+        if self.backend not in ("auto", "nccl", "nvls"):
+            raise ValueError(f"unknown all-reduce backend {self.backend!r}")
+        self.nvls_blocks = int(os.environ.get("SPF_NVLS_BLOCKS", nvls_blocks or 16))
+        self._symm: Dict[int, tuple] = {}      # data_ptr -> (tensor, symmetric-memory handle)
+        self.nvls_error: Optional[str] = None  # why "auto" fell back to nccl, if it did
+
+    # ---- symmetric-memory buckets (NVLS path) ----------------------------------------------------------------
+    def alloc(self, numel: int, dtype: torch.dtype = torch.float32) -> Tensor:
+        """A zero-filled gradient bucket.  With the nvls backend (CUDA, world > 1, multicast available) it is
+        symmetric memory bound to the group's multicast object and `launch([bucket])` reduces it in the switch;
+        otherwise a plain tensor reduced by torch.distributed.  COLLECTIVE: every rank must call it, same sizes."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        want = self.backend in ("auto", "nvls") and self.device.type == "cuda" and world > 1 and dtype == torch.float32
+        if want:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                padded = (numel + 3) // 4 * 4
+                with torch.cuda.device(self.device):
+                    t = symm_mem.empty(padded, dtype=dtype, device=self.device)
+                    hdl = symm_mem.rendezvous(t, group=self.group if self.group is not None else dist.group.WORLD)
+                if not int(hdl.multicast_ptr):
+                    raise RuntimeError("symmetric memory has no multicast binding (no NVSwitch multicast support)")
+                self._symm[t.data_ptr()] = (t, hdl)
+                ok, why = self._self_test(t, world), "multimem self-test gave wrong sums"
+            except Exception as exc:        # noqa: BLE001 -- anything here means "no NVLS on this machine"
+                ok, why = False, f"{type(exc).__name__}: {exc}"
+            # the choice of backend must be the same on every rank
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 1:
+                t.zero_()
+                return t[:numel]
+            self._symm.clear()
+            if self.backend == "nvls":
+                raise RuntimeError(f"nvls all-reduce unavailable: {why if not ok else 'another rank failed'}")
+            self.nvls_error = why if not ok else "another rank failed"
+        elif self.backend == "nvls" and world > 1:
+            raise RuntimeError("nvls all-reduce needs CUDA fp32 buckets")
+        return torch.zeros(numel, dtype=dtype, device=self.device)
+
+    def _self_test(self, t: Tensor, world: int) -> bool:
+        """rank r fills its bucket with r+1 (+ a position ramp); after the reduction every element must hold the sum."""
+        rank = dist.get_rank(self.group)
+        ramp = (torch.arange(t.numel(), device=self.device, dtype=torch.float32) % 64.0)
+        t.copy_(ramp * (rank + 1) + (rank + 1))
+        self._launch_nvls(t)
+        self.wait()
+        tri = world * (world + 1) // 2
+        good = bool(torch.equal(t, ramp * tri + tri))
+        torch.cuda.synchronize(self.device)
+        return good
+
+    def uses_nvls(self, t: Tensor) -> bool:
+        return t.data_ptr() in self._symm
+
+    @staticmethod
+    def _mc_offset(hdl) -> int:
+        # torch >= 2.8 pools symmetric allocations: the handle's multicast address is the pool block's, the tensor
+        # sits `offset` bytes into it
+        return int(getattr(hdl, "offset", 0) or 0)
+
+    def _launch_nvls(self, g: Tensor) -> None:
+        from . import _lib
+        t, hdl = self._symm[g.data_ptr()]
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            hdl.barrier(channel=0)           # every rank's bucket is final
+            _lib.check(_lib.lib().spf_multimem_allreduce_f32(
+                ctypes.c_void_p(int(hdl.multicast_ptr) + int(self._mc_offset(hdl))), t.numel(), int(hdl.rank), int(hdl.world_size),
+                self.nvls_blocks, ctypes.c_void_p(self.stream.cuda_stream)), "spf_multimem_allreduce_f32")
+            hdl.barrier(channel=0)           # every slice has been broadcast to every rank
 
     def _ensure_bucket(self, numel: int, dtype: torch.dtype):
         if self._bucket is None or self._bucket.numel() < numel or self._bucket.dtype != dtype:
@@ -64,6 +145,9 @@ class GradAllReduce:
             # a single tensor IS the bucket: reduce it in place
             g = grads[0]
             self._views = []
+            if self._symm and g.data_ptr() in self._symm:
+                self._launch_nvls(g)
+                return
             if self.stream is not None:
                 self.stream.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(self.stream):

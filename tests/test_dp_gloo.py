@@ -84,3 +84,30 @@ def test_sharded_views_allreduce_equals_single_process(tmp_path, n_views):
             assert torch.allclose(got[r][k], t.grad, rtol=1e-5, atol=1e-6 * float(t.grad.abs().max())), (k, r)
         assert torch.equal(got[0][k], got[1][k])          # every rank ends with the same reduced gradient
     assert got[0]["_loss"].item() == pytest.approx(total.item(), rel=1e-5)
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        red = GradAllReduce(torch.device("cpu"))              # "auto": no CUDA here -> plain bucket, gloo reduction
+        buf = red.alloc(1001)
+        assert buf.shape == (1001,) and not red.uses_nvls(buf) and float(buf.abs().sum()) == 0.0
+        buf += torch.arange(1001, dtype=torch.float32) * (rank + 1)
+        red.launch([buf])
+        red.wait()
+        torch.save(buf, os.path.join(out_dir, f"bucket{rank}.pt"))
+        with pytest.raises(RuntimeError):
+            GradAllReduce(torch.device("cpu"), backend="nvls").alloc(16)   # the in-switch kernel needs CUDA buckets
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucket_alloc_falls_back_to_the_process_group_without_nvswitch(tmp_path):
+    world = 2
+    mp.spawn(_bucket_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = torch.arange(1001, dtype=torch.float32) * 3
+    for r in range(world):
+        assert torch.equal(torch.load(os.path.join(str(tmp_path), f"bucket{r}.pt")), want)
+    with pytest.raises(ValueError):
+        GradAllReduce(torch.device("cpu"), backend="rdma")
