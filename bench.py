@@ -145,6 +145,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None
+    if world > 1 and os.environ.get("SPF_NUMA_BIND", "1") != "0":
+        from spfsplatv2_b200.dp import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)      # before any pinned allocation: keeps H2D traffic on-socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     v_cxt, h, w, b, desc = WORKLOADS[args.workload]
@@ -316,7 +320,8 @@ def run_ours(args):
                        "parallelism": f"dp{world} (scenes sharded over ranks; 64 MiB stand-in grad all-reduce/step, {ar_backend})" if world > 1 else "single GPU",
                        "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step > 126 MB L2, no explicit flush",
                        "loop": "one CUDA graph per step (fwd + fused MSE + bwd)" if graphed else "eager PyTorch loop",
-                       "loss": "fused MSE (spfsplatv2_b200.loss.mse_loss)"},
+                       "loss": "fused MSE (spfsplatv2_b200.loss.mse_loss)",
+                       "numa_node_rank0": numa_node},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(max(ms_e2e, wall_e2e) / args.steps, 4)},
             "gpu_launches": (13 + (1 if ar_backend == "nvls" else 0)) * args.steps,   # (+ the multimem all-reduce kernel at N>1) camera fwd/bwd, project fwd/bwd, scan, emit, sort+pack, blend fwd, blend bwd (log + fallback), pose reduce, fused MSE loss (2)

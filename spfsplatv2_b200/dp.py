@@ -37,6 +37,39 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process (and therefore its pinned-host-memory pages, first-touch) to the CPUs of the NUMA node the
+    GPU's PCIe root port hangs off, so that every rank's host->device copies stay on its own socket instead of
+    crossing the inter-socket link.  torchrun does not do this.  Call before allocating pinned buffers.
+    Returns the node, or None when the topology cannot be read (no GPU, no sysfs, single node) -- never raises."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set(_parse_cpulist(f.read()))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:       # noqa: BLE001
+        return None
+
+
 class GradAllReduce:
     """Sum-all-reduce of a set of gradient tensors, flattened into one bucket, launched on a side stream as soon
     as the producer (projection backward) has been enqueued; `wait()` joins it back into the current stream.
