@@ -70,13 +70,14 @@ __device__ void block_exclusive_scan(const int* __restrict__ in, int* __restrict
 __global__ void __launch_bounds__(1024)
 scan_kernel(const int* block_sum, int* block_off, int64_t n_blocks, const int* tile_count,
             int* tile_start, int64_t n_tiles, int* n_total, int* host_counters, int ticket) {
+  pdl_enter();
   if (blockIdx.x == 0) block_exclusive_scan(block_sum, block_off, n_blocks, n_total, host_counters, ticket);
   else block_exclusive_scan(tile_count, tile_start, n_tiles, nullptr, nullptr, 0);
 }
 
 cudaError_t launch_scan(const Dims& d, const SpfRasterState& st, const ControlLayout& cl, cudaStream_t s) {
   int* c = st.control;
-  scan_kernel<<<2, 1024, 0, s>>>(c + cl.block_sum, c + cl.block_off, (int64_t)d.B * d.NB, c + cl.tile_count,
+  pdl_launch(scan_kernel, 2, 1024, 0, s)(c + cl.block_sum, c + cl.block_off, (int64_t)d.B * d.NB, c + cl.tile_count,
                                  c + cl.tile_start, (int64_t)d.B * d.T, c + cl.n_total, st.host_counters,
                                  d.ticket);
   return cudaGetLastError();
@@ -97,6 +98,7 @@ __device__ __forceinline__ void rect_of(float px, float py, int radius, int gx, 
 __global__ void __launch_bounds__(PROJ_THREADS)
 emit_kernel(Dims d, SpfRasterState st, const int* __restrict__ block_off, const int* __restrict__ tile_start,
             int* __restrict__ tile_cursor, int* __restrict__ overflow) {
+  pdl_enter();
   __shared__ int warp_part[PROJ_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int view = blockIdx.y;
@@ -143,7 +145,7 @@ emit_kernel(Dims d, SpfRasterState st, const int* __restrict__ block_off, const 
 cudaError_t launch_emit(const Dims& d, const SpfRasterState& st, const ControlLayout& cl, cudaStream_t s) {
   int* c = st.control;
   dim3 grid(d.NB, d.B);
-  emit_kernel<<<grid, PROJ_THREADS, 0, s>>>(d, st, c + cl.block_off, c + cl.tile_start, c + cl.tile_cursor,
+  pdl_launch(emit_kernel, grid, PROJ_THREADS, 0, s)(d, st, c + cl.block_off, c + cl.tile_start, c + cl.tile_cursor,
                                             c + cl.overflow);
   return cudaGetLastError();
 }
@@ -250,6 +252,7 @@ __device__ __forceinline__ void pack_records(const Dims& d, const SpfRasterState
 template <int CAP, int NBK>
 __global__ void __launch_bounds__(TILE_THREADS)
 tile_sort_pack_kernel(Dims d, SpfRasterState st, const int* __restrict__ tile_start) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];
   SortSmem<CAP, NBK>& S = *reinterpret_cast<SortSmem<CAP, NBK>*>(sort_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -357,7 +360,7 @@ static cudaError_t launch_tsp(const Dims& d, const SpfRasterState& st, const Con
   const size_t smem = sizeof(SortSmem<CAP, NBK>);
   cudaError_t e = cudaFuncSetAttribute(tile_sort_pack_kernel<CAP, NBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tile_sort_pack_kernel<CAP, NBK><<<d.B * d.T, TILE_THREADS, smem, s>>>(d, st, st.control + cl.tile_start);
+  pdl_launch(tile_sort_pack_kernel<CAP, NBK>, d.B * d.T, TILE_THREADS, smem, s)(d, st, st.control + cl.tile_start);
   return cudaGetLastError();
 }
 
@@ -375,6 +378,7 @@ cudaError_t launch_tile_sort_pack(const Dims& d, const SpfRasterState& st, const
 // ---- parity helper: (point_list, keys) out of the slab -------------------------------------------
 __global__ void unpack_sorted_kernel(Dims d, SpfRasterState st, const int* __restrict__ tile_start,
                                      int64_t n, int32_t* point_list, uint64_t* keys) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 c = reinterpret_cast<const float4*>(st.slab)[3 * i + 2];
@@ -395,7 +399,7 @@ cudaError_t launch_unpack_sorted(const Dims& d, const SpfRasterState& st, int64_
                                  uint64_t* keys, const ControlLayout& cl, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   const int threads = 256;
-  unpack_sorted_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(
+  pdl_launch(unpack_sorted_kernel, (unsigned)((n + threads - 1) / threads), threads, 0, s)(
       d, st, st.control + cl.tile_start, n, point_list, keys);
   return cudaGetLastError();
 }

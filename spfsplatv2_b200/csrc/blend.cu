@@ -82,6 +82,7 @@ constexpr unsigned PAIR_SKIP = 0xffffffffu;   // word0 of a padding record: the 
 template <bool TMA, bool LOG>
 __global__ void __launch_bounds__(TILE_THREADS)
 blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterOut out) {
+  pdl_enter();
   __shared__ __align__(128) float4 buf[2][CH_F * 3];
   __shared__ __align__(128) float4 box[2][CH_F];
   __shared__ __align__(8) uint64_t bar[2];
@@ -227,11 +228,11 @@ cudaError_t launch_blend_forward(const Dims& d, const SpfRasterIn& in, const Spf
   const int grid = d.B * d.T;
   const bool log = st.pair_log != nullptr && st.pair_count != nullptr && d.pair_cap > 0;
   if (d.flags & SPF_FLAG_NO_TMA) {
-    if (log) blend_forward_kernel<false, true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
-    else blend_forward_kernel<false, false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+    if (log) pdl_launch(blend_forward_kernel<false, true>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
+    else pdl_launch(blend_forward_kernel<false, false>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
   } else {
-    if (log) blend_forward_kernel<true, true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
-    else blend_forward_kernel<true, false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, out);
+    if (log) pdl_launch(blend_forward_kernel<true, true>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
+    else pdl_launch(blend_forward_kernel<true, false>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
   }
   return cudaGetLastError();
 }
@@ -276,6 +277,7 @@ template <bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS)
 blend_backward_v1_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                       float* __restrict__ dup_grad) {
+  pdl_enter();
   __shared__ __align__(128) float4 buf[2][CH_B * 3];
   __shared__ __align__(128) float4 box[2][CH_B];
   __shared__ __align__(8) uint64_t bar[2];
@@ -653,6 +655,7 @@ template <bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS, 3)
 blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                       float* __restrict__ dup_grad, int use_log) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
   const int n_tiles = d.B * d.T;
@@ -693,6 +696,7 @@ struct LogSmem {
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                           float* __restrict__ dup_grad) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LogSmem& S = *reinterpret_cast<LogSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -887,9 +891,9 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
   const int grid = d.B * d.T;
   if (d.flags & SPF_FLAG_BWD_V1) {
     if (d.flags & SPF_FLAG_NO_TMA)
-      blend_backward_v1_kernel<false><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+      pdl_launch(blend_backward_v1_kernel<false>, grid, TILE_THREADS, 0, s)(d, in.bg, st, gout, gin.dup_grad);
     else
-      blend_backward_v1_kernel<true><<<grid, TILE_THREADS, 0, s>>>(d, in.bg, st, gout, gin.dup_grad);
+      pdl_launch(blend_backward_v1_kernel<true>, grid, TILE_THREADS, 0, s)(d, in.bg, st, gout, gin.dup_grad);
     return cudaGetLastError();
   }
   const bool use_log = st.pair_log != nullptr && st.pair_count != nullptr && d.pair_cap > 0;
@@ -897,7 +901,7 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
     cudaError_t e0 = cudaFuncSetAttribute(blend_backward_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(LogSmem));
     if (e0 != cudaSuccess) return e0;
-    blend_backward_log_kernel<<<grid, TILE_THREADS, sizeof(LogSmem), s>>>(d, in.bg, st, gout, gin.dup_grad);
+    pdl_launch(blend_backward_log_kernel, grid, TILE_THREADS, sizeof(LogSmem), s)(d, in.bg, st, gout, gin.dup_grad);
     e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
   }
@@ -907,11 +911,11 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
   if (d.flags & SPF_FLAG_NO_TMA) {
     e = cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    blend_backward_kernel<false><<<grid2, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
+    pdl_launch(blend_backward_kernel<false>, grid2, TILE_THREADS, smem, s)(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
   } else {
     e = cudaFuncSetAttribute(blend_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    blend_backward_kernel<true><<<grid2, TILE_THREADS, smem, s>>>(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
+    pdl_launch(blend_backward_kernel<true>, grid2, TILE_THREADS, smem, s)(d, in.bg, st, gout, gin.dup_grad, use_log ? 1 : 0);
   }
   return cudaGetLastError();
 }

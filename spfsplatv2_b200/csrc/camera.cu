@@ -4,6 +4,7 @@
 // scale-invariance of the extrinsics (/root/reference/src/model/decoder/cuda_splatting.py:66-74),
 // get_fov (src/geometry/projection.py:269-283), get_projection_matrix (cuda_splatting.py:15-42) and
 // extrinsics.inverse() + the two transposes (cuda_splatting.py:88-90).
+#include "spf_device.cuh"
 #include "spf_kernels.h"
 
 namespace spf {
@@ -47,6 +48,7 @@ __global__ void camera_forward_kernel(int B, int scale_invariant, const float* _
                                       const float* __restrict__ far, float* __restrict__ view,
                                       float* __restrict__ proj, float* __restrict__ tanfov,
                                       float* __restrict__ pre_scale) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float n = near[i], f = far[i];
@@ -94,6 +96,7 @@ __global__ void camera_forward_kernel(int B, int scale_invariant, const float* _
 __global__ void camera_backward_kernel(int B, int scale_invariant, const float* __restrict__ near,
                                        const float* __restrict__ view, const float* __restrict__ d_view,
                                        float* __restrict__ d_ext) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float Mt[16], G[16];   // Mt = M^T = view ; G = dL/dM = (dL/dview)^T
@@ -121,13 +124,13 @@ __global__ void camera_backward_kernel(int B, int scale_invariant, const float* 
 cudaError_t launch_camera_forward(int B, int scale_invariant, const float* ext, const float* intr,
                                   const float* near, const float* far, float* view, float* proj, float* tanfov,
                                   float* pre_scale, cudaStream_t s) {
-  camera_forward_kernel<<<(B + 63) / 64, 64, 0, s>>>(B, scale_invariant, ext, intr, near, far, view, proj, tanfov,
+  pdl_launch(camera_forward_kernel, (B + 63) / 64, 64, 0, s)(B, scale_invariant, ext, intr, near, far, view, proj, tanfov,
                                                      pre_scale);
   return cudaGetLastError();
 }
 cudaError_t launch_camera_backward(int B, int scale_invariant, const float* near, const float* view,
                                    const float* d_view, float* d_ext, cudaStream_t s) {
-  camera_backward_kernel<<<(B + 63) / 64, 64, 0, s>>>(B, scale_invariant, near, view, d_view, d_ext);
+  pdl_launch(camera_backward_kernel, (B + 63) / 64, 64, 0, s)(B, scale_invariant, near, view, d_view, d_ext);
   return cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@ constexpr int LOSS_THREADS = 256;
 __global__ void __launch_bounds__(LOSS_THREADS)
 image_mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_per_image, int clip,
                          float grad_scale, float* __restrict__ dL_dpred, float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float warp_part[LOSS_THREADS / 32];
   const int img = blockIdx.y;
   const int64_t base = (int64_t)img * n_per_image;
@@ -61,6 +62,7 @@ image_mse_partial_kernel(const float* __restrict__ pred, const float* __restrict
 __global__ void image_mse_final_kernel(const float* __restrict__ partial, int blocks_per_image, int n_images,
                                        float inv_n_per_image, float* __restrict__ mse_per_image,
                                        float* __restrict__ mean_all) {
+  pdl_enter();
   // one warp per image, then lane 0 of warp 0 averages the images in order
   __shared__ float per_img[1024];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -85,10 +87,10 @@ cudaError_t launch_image_mse(const float* pred, const float* target, int n_image
                              float grad_scale, float* dL_dpred, float* partial, int blocks_per_image,
                              float* mse_per_image, float* mean_all, cudaStream_t s) {
   dim3 grid(blocks_per_image, n_images);
-  image_mse_partial_kernel<<<grid, LOSS_THREADS, 0, s>>>(pred, target, n_per_image, clip, grad_scale, dL_dpred, partial);
+  pdl_launch(image_mse_partial_kernel, grid, LOSS_THREADS, 0, s)(pred, target, n_per_image, clip, grad_scale, dL_dpred, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  image_mse_final_kernel<<<1, 256, 0, s>>>(partial, blocks_per_image, n_images, 1.0f / (float)n_per_image, mse_per_image,
+  pdl_launch(image_mse_final_kernel, 1, 256, 0, s)(partial, blocks_per_image, n_images, 1.0f / (float)n_per_image, mse_per_image,
                                            mean_all);
   return cudaGetLastError();
 }

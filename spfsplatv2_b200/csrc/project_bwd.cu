@@ -29,6 +29,7 @@ namespace spf {
 template <bool MULTI>
 __global__ void __launch_bounds__(PROJ_THREADS, MULTI ? 2 : 5)
 project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGradIn gin) {
+  pdl_enter();
   extern __shared__ __align__(128) float smem[];
   __shared__ ViewConsts vc;
   __shared__ float pose_warp[PROJ_THREADS / 32][15];
@@ -220,6 +221,7 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
 __global__ void __launch_bounds__(256)
 pose_reduce_kernel(Dims d, const float* __restrict__ viewmatrix, const float* __restrict__ partial,
                    float* __restrict__ dV) {
+  pdl_enter();
   __shared__ float red[16][15];
   const int view = blockIdx.x, tid = threadIdx.x;
   const int c = tid % 15, part = tid / 15;
@@ -264,7 +266,7 @@ static cudaError_t launch_pb(const Dims& d, const SpfRasterIn& in, const SpfRast
     if (e != cudaSuccess) return e;
   }
   dim3 grid(d.NB, d.S);
-  project_backward_kernel<MULTI><<<grid, PROJ_THREADS, smem, s>>>(d, in, st, gin);
+  pdl_launch(project_backward_kernel<MULTI>, grid, PROJ_THREADS, smem, s)(d, in, st, gin);
   return cudaGetLastError();
 }
 
@@ -274,7 +276,7 @@ cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const 
 }
 
 cudaError_t launch_pose_reduce(const Dims& d, const SpfRasterIn& in, const SpfRasterGradIn& gin, cudaStream_t s) {
-  pose_reduce_kernel<<<d.B, 256, 0, s>>>(d, in.viewmatrix, gin.pose_partial, gin.dL_dviewmatrix);
+  pdl_launch(pose_reduce_kernel, d.B, 256, 0, s)(d, in.viewmatrix, gin.pose_partial, gin.dL_dviewmatrix);
   return cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@ namespace spf {
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
                        int* __restrict__ block_sum) {
+  pdl_enter();
   extern __shared__ __align__(128) float sh_s[];
   __shared__ ViewConsts vc;
   __shared__ __align__(8) uint64_t bar;
@@ -159,6 +160,7 @@ struct PFSmem {
 __global__ void __launch_bounds__(2 * PROJ_THREADS, 2)
 project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
                               int* __restrict__ block_sum) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
   PFSmem& S = *reinterpret_cast<PFSmem*>(pf_smem_raw);
   const int tid = threadIdx.x;
@@ -287,12 +289,12 @@ cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const S
                                          (int)sizeof(PFSmem));
     if (e != cudaSuccess) return e;
     const int grid1 = min(d.B * d.NB, 2 * 148);
-    project_forward_stream_kernel<<<grid1, 2 * PROJ_THREADS, sizeof(PFSmem), s>>>(d, in, st, st.control + cl.tile_count,
+    pdl_launch(project_forward_stream_kernel, grid1, 2 * PROJ_THREADS, sizeof(PFSmem), s)(d, in, st, st.control + cl.tile_count,
                                                                              st.control + cl.block_sum);
     return cudaGetLastError();
   }
   dim3 grid(d.NB, d.B);
-  project_forward_kernel<<<grid, PROJ_THREADS, smem, s>>>(d, in, st, st.control + cl.tile_count,
+  pdl_launch(project_forward_kernel, grid, PROJ_THREADS, smem, s)(d, in, st, st.control + cl.tile_count,
                                                           st.control + cl.block_sum);
   return cudaGetLastError();
 }

@@ -10,6 +10,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------
+// First statement of every raster-path kernel (see pdl_launch in spf_kernels.h): wait until the preceding kernel in the
+// stream has completed and its writes are visible, then allow the following kernel's CTAs to be scheduled into free SM
+// slots.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "../../include/spfsplat.h"
 
@@ -39,6 +42,47 @@ struct Dims {
   int ticket;
   int pair_cap;   // pair-log records per warp (0 = no log)
 };
+
+// Programmatic dependent launch (PDL, sm_90+): every kernel of the raster path is launched with the
+// programmatic-stream-serialization attribute and starts with `pdl_enter()` (spf_device.cuh: griddepcontrol.wait, then
+// griddepcontrol.launch_dependents).  The next kernel's CTAs are scheduled into SM slots as they free up during the
+// current kernel's last wave and park at the wait until the current kernel has completed and flushed, so the launch
+// latency and the CTA ramp of each of the ~13 kernels of a step disappear from the critical path (also inside a
+// captured CUDA graph, where the dependency becomes a programmatic edge).  Every kernel in the chain executes the wait,
+// so completion stays transitive.  SPF_PDL=0 falls back to plain stream order.
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPF_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename K>
+struct PdlLaunch {
+  K kernel;
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+  template <typename... A>
+  void operator()(A&&... args) const {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);   // callers read cudaGetLastError()
+  }
+};
+template <typename K>
+inline PdlLaunch<K> pdl_launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+  return PdlLaunch<K>{kernel, grid, block, smem, stream};
+}
 
 cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                    const ControlLayout& cl, cudaStream_t s);
