@@ -111,3 +111,13 @@ def test_bucket_alloc_falls_back_to_the_process_group_without_nvswitch(tmp_path)
         assert torch.equal(torch.load(os.path.join(str(tmp_path), f"bucket{r}.pt")), want)
     with pytest.raises(ValueError):
         GradAllReduce(torch.device("cpu"), backend="rdma")
+
+
+def test_numa_binding_helper_is_a_safe_no_op_without_topology():
+    from spfsplatv2_b200.dp import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)   # never raises
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
