@@ -103,6 +103,7 @@ class GradAllReduce:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         want = self.backend in ("auto", "nvls") and self.device.type == "cuda" and world > 1 and dtype == torch.float32
         if want:
+            t, why = None, None
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 padded = (numel + 3) // 4 * 4
@@ -111,23 +112,33 @@ class GradAllReduce:
                     hdl = symm_mem.rendezvous(t, group=self.group if self.group is not None else dist.group.WORLD)
                 if not int(hdl.multicast_ptr):
                     raise RuntimeError("symmetric memory has no multicast binding (no NVSwitch multicast support)")
-                self._symm[t.data_ptr()] = (t, hdl)
-                ok, why = self._self_test(t, world), "multimem self-test gave wrong sums"
             except Exception as exc:        # noqa: BLE001 -- anything here means "no NVLS on this machine"
-                ok, why = False, f"{type(exc).__name__}: {exc}"
-            # the choice of backend must be the same on every rank
-            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            if int(flag.item()) == 1:
-                t.zero_()
-                return t[:numel]
+                why = f"{type(exc).__name__}: {exc}"
+            # The backend must be the same on every rank, and the self-test below is itself collective: agree first
+            # that every rank has its bucket, then that every rank saw the right sums.
+            if self._all_ranks(why is None):
+                self._symm[t.data_ptr()] = (t, hdl)
+                try:
+                    if not self._self_test(t, world):
+                        why = "multimem self-test gave wrong sums"
+                except Exception as exc:    # noqa: BLE001
+                    why = f"{type(exc).__name__}: {exc}"
+                if self._all_ranks(why is None):
+                    t.zero_()
+                    return t[:numel]
             self._symm.clear()
+            why = why or "another rank failed"
             if self.backend == "nvls":
-                raise RuntimeError(f"nvls all-reduce unavailable: {why if not ok else 'another rank failed'}")
-            self.nvls_error = why if not ok else "another rank failed"
+                raise RuntimeError(f"nvls all-reduce unavailable: {why}")
+            self.nvls_error = why
         elif self.backend == "nvls" and world > 1:
             raise RuntimeError("nvls all-reduce needs CUDA fp32 buckets")
         return torch.zeros(numel, dtype=dtype, device=self.device)
+
+    def _all_ranks(self, ok: bool) -> bool:
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return int(flag.item()) == 1
 
     def _self_test(self, t: Tensor, world: int) -> bool:
         """rank r fills its bucket with r+1 (+ a position ramp); after the reduction every element must hold the sum."""
