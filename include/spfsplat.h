@@ -68,7 +68,7 @@ typedef struct {
   float   scale_modifier;    /* settings.scale_modifier */
   int64_t dup_capacity;      /* capacity (records) of bucket / slab / dup_grad buffers */
   int32_t ticket;            /* written next to N into state.host_counters (see there) */
-  int32_t pair_capacity;     /* pair-log records per warp (state.pair_log); 0 = no pair log */
+  int32_t pair_capacity;     /* pair-log entries (8 B) per warp (state.pair_log); 0 = no pair log */
 } SpfRasterDesc;
 
 /* Inputs (forward kwargs of GaussianRasterizer.__call__, cuda_splatting.py:128-138, batched). */
@@ -109,9 +109,9 @@ typedef struct {
   int32_t*  n_contrib;       /* [B,H,W] */
   float*    accum;           /* [B,H,W,4] blended sums (rgb, depth) WITHOUT the background term; written by
                                 forward, read by backward (16-byte aligned) */
-  void*     pair_log;        /* NULL, or [B*T*8, pair_capacity, 32 B]: per-warp log of contributing (pixel,
-                                Gaussian) pairs written by the forward blend, consumed by the backward (private
-                                layout).  NULL => the backward recomputes them (slower). */
+  void*     pair_log;        /* NULL, or [B*T*8, pair_capacity, 8 B]: per-warp log of contributing (pixel,
+                                Gaussian) pairs {record index | pixel lane << 25, exp(power)} written by the forward
+                                blend, consumed by the backward.  NULL => the backward recomputes them (slower). */
   int32_t*  pair_count;      /* NULL, or [B*T*8]: pairs logged per warp, -1 = capacity exceeded (that tile falls
                                 back to recomputation); control[2] = largest count needed by any warp */
   int32_t*  host_counters;   /* NULL, or 2 int32 of device-mapped PINNED HOST memory: the scan kernel

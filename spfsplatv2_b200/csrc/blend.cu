@@ -69,25 +69,70 @@ __device__ __forceinline__ bool box_hits(const float4& bb, float x0, float x1, f
   return (bb.x <= x1) && (bb.y >= x0) && (bb.z <= y1) && (bb.w >= y0);
 }
 
-// Pair log (LOG = true, enabled when a backward pass will follow): every warp appends one 32-byte record per
-// CONTRIBUTING (pixel, Gaussian) pair, in hit order (pairs of one Gaussian adjacent, in lane order):
-//   word0 = record index in the tile list | lane << 25;  G;  T_before;  the blended sums (rgb, depth) AFTER this pair.
-// Runs are padded so that none straddles a 32-record boundary of the log (PAIR_SKIP marker).
-// With these the backward needs no per-pixel sequential pass at all (see blend_backward_log_kernel).  A warp's
-// segment holds `pair_capacity` records; a warp that needs more stops writing and reports -1 (its tile is then
-// handled by the recomputing v2 backward).  The largest per-warp count goes to control[2] for the host's sizing.
+// Integer pixel rectangle of a record's alpha box inside a warp region [x0,x1]x[y0,y1] (pixel centres are the integer
+// coordinates; the region bounds are already clipped to the image).  The boxes are conservative, so a record whose
+// rectangle is empty cannot contribute to any pixel of the region.  Forward and backward share this test: the
+// backward's per-record region masks must cover every region whose warp logged a pair of the record.
+__device__ __forceinline__ bool region_rect(const float4& bb, float x0, float x1, float y0, float y1, float& fx0,
+                                            float& fx1, float& fy0, float& fy1) {
+  fx0 = fmaxf(ceilf(bb.x), x0);
+  fx1 = fminf(floorf(bb.y), x1);
+  fy0 = fmaxf(ceilf(bb.z), y0);
+  fy1 = fminf(floorf(bb.w), y1);
+  return (fx0 <= fx1) && (fy0 <= fy1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Blend forward, v4: PAIR-PARALLEL alpha evaluation, per-pixel queues for the (order-dependent) compositing.
+//
+// With SPFSplatV2's splat sizes a warp region (8x4 pixels) is touched by ~57 records of a tile's ~370, and a touched
+// record covers ~5.6 of the region's 32 pixel centres, ~4.3 of which pass the alpha test (scripts/pair_stats.py).  The
+// previous kernel spent one 32-lane iteration per touched record at 4/32 useful lanes.  Here a warp works in two
+// alternating phases:
+//
+//   phase A (lane = candidate (record, pixel) pair).  32 records are culled at a time, one per lane: the integer
+//       pixel rectangle of the record's alpha box inside the region (region_rect) gives n = w*h candidates; a warp
+//       scan of n and a bit mask of run heads (redux.or) let lane l of a batch find the record and the pixel of
+//       candidate number 32*batch + l.  Each lane evaluates ONE alpha; contributing pairs are appended, in
+//       (record, pixel) order, to the queue of their pixel (match.any ranks same-pixel pairs of a batch) and, if a
+//       backward follows, to the warp's pair log.
+//   phase B (lane = pixel).  Every pixel composites its queue front to back (T, colour, depth, early stop, last
+//       contributor) -- ~14 instructions per pair.  Queues are drained when one fills up, before the staged records
+//       they point to are recycled, and at the end of the list.
+//
+// A cull group whose records cover most of the region (large splats: mean candidates per touched record >= DENSE_MIN)
+// takes the DENSE path instead -- one record per iteration, every lane evaluates its own pixel and composites at
+// once -- after the queues have been drained, so the per-pixel order is always the list order.  The arithmetic per
+// (pixel, record) is the same in both paths and the accept / reject decisions are the per-pixel tests of eval_alpha,
+// so images, final_T and n_contrib do not depend on the path taken.
+//
+// Pair log (LOG = true): one 8-byte entry per contributing pair, dense, in (record, pixel-lane) order:
+//   x = record index in the tile list | pixel lane << 25,  y = G = exp(power).
+// Pairs logged for a pixel after it stopped (possible only between two drains) carry a record index >= that pixel's
+// n_contrib; the backward ignores them.  A warp's segment holds `pair_capacity` entries; a warp that needs more stops
+// writing and reports -1 (its tile is then handled by the recomputing backward).  control[2] = largest count needed.
 constexpr unsigned PAIR_J_MASK = (1u << 25) - 1u;
-constexpr unsigned PAIR_SKIP = 0xffffffffu;   // word0 of a padding record: the rest of this 32-record block is unused
+constexpr int QD = 8;            // queue slots per pixel
+constexpr int DENSE_MIN = 12;    // mean candidates per touched record from which a cull group takes the dense path
+constexpr unsigned FULL = 0xffffffffu;
+
+struct FwdSmem {
+  float4 buf[2][CH_F * 3];       // staged slab records
+  float4 box[2][CH_F];           // staged alpha boxes
+  uint2 queue[8][QD * 32];       // per warp: [slot][pixel] = {alpha, record index in the tile list}
+  uint32_t hits[8][32];          // per warp: touched records of the current cull group (packed rectangle + prefix)
+  int qcnt[8][32];               // per warp: queued pairs per pixel
+  uint64_t bar[2];
+  int blk_pairs;
+};
 
 template <bool TMA, bool LOG>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterOut out) {
   pdl_enter();
-  __shared__ __align__(128) float4 buf[2][CH_F * 3];
-  __shared__ __align__(128) float4 box[2][CH_F];
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ int blk_pairs;
-  const int tid = threadIdx.x, lane = tid & 31;
+  extern __shared__ __align__(128) unsigned char fwd_smem_raw[];
+  FwdSmem& S = *reinterpret_cast<FwdSmem*>(fwd_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int t = blockIdx.x;
   const int view = t / d.T, tile = t - view * d.T;
   const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
@@ -97,112 +142,206 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   const int px = bx + (lane & 7), py = by + (lane >> 3);
   const bool inside = (px < d.W) && (py < d.H);
   const float pxf = (float)px, pyf = (float)py;
-  const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
-  if (TMA || LOG) {
-    if (tid == 0) {
-      if (TMA) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
-      blk_pairs = 0;
-    }
-    __syncthreads();
+  // the warp's region, clipped to the image (empty if the region lies outside: no candidates are ever generated)
+  const float wx0 = (float)bx, wx1 = (float)min(bx + 7, d.W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, d.H - 1);
+  if (tid == 0) {
+    if (TMA) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
+    S.blk_pairs = 0;
   }
+  uint2* q = S.queue[wid];
+  int* qc = S.qcnt[wid];
+  uint32_t* hits = S.hits[wid];
+  qc[lane] = 0;
+  __syncthreads();
   const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
   const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
   const int nchunks = (L + CH_F - 1) / CH_F;
   const int Cw = d.pair_cap;
-  uint4* plog = LOG ? reinterpret_cast<uint4*>(st.pair_log) + ((size_t)t * 8 + (tid >> 5)) * (size_t)Cw * 2 : nullptr;
+  uint2* plog = LOG ? reinterpret_cast<uint2*>(st.pair_log) + ((size_t)t * 8 + wid) * (size_t)Cw : nullptr;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned lane_bits = (unsigned)lane << 25;
-  int room = Cw;   // pair-log records this warp may still write
+  int npairs = 0;    // pairs this warp has produced for the log (keeps counting past the capacity)
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
   int last = 0;
   bool done = !inside;
-  int pending = -1;  // chunk whose TMA load is in flight beyond the current one
+  unsigned donemask = __ballot_sync(FULL, done);
+  bool queued = false;   // warp-uniform: some queue is non-empty
+  int pending = -1;      // chunk whose TMA load is in flight beyond the current one
+
+  // phase B: every pixel composites its queued pairs in list order
+  auto drain = [&]() {
+    const int n = qc[lane];
+    const int maxn = __reduce_max_sync(FULL, n);
+    for (int i = 0; i < maxn; ++i) {
+      if (i < n && !done) {
+        const uint2 en = q[i * 32 + lane];
+        const float alpha = __uint_as_float(en.x);
+        const unsigned idx = en.y;
+        const float test_T = T * (1.0f - alpha);
+        if (test_T < T_STOP) {
+          done = true;
+        } else {
+          const float4* r = S.buf[(idx / CH_F) & 1u] + 3u * (idx % CH_F);
+          const float2 c01 = *reinterpret_cast<const float2*>(&r[1].z);
+          const float2 c2d = *reinterpret_cast<const float2*>(&r[2].x);
+          const float w = alpha * T;
+          C0 += c01.x * w; C1 += c01.y * w; C2 += c2d.x * w; D += c2d.y * w;
+          T = test_T;
+          last = (int)idx + 1;
+        }
+      }
+    }
+    qc[lane] = 0;
+    queued = false;
+    donemask = __ballot_sync(FULL, done);
+    __syncwarp();
+  };
 
   // Lists of at most two chunks (the common case) live entirely in the two buffers: nothing is ever refilled, so the
   // warps need no block barrier at all -- each waits on the chunk's mbarrier and leaves as soon as ITS 32 pixels are
   // done.  Longer lists recycle the buffers and keep the block in step.
   const bool free_running = TMA && (nchunks <= 2);
-  if (nchunks > 0) stage_chunk<TMA>(buf[0], box[0], slab, cull, min(CH_F, L), &bar[0], tid);
+  if (nchunks > 0) stage_chunk<TMA>(S.buf[0], S.box[0], slab, cull, min(CH_F, L), &S.bar[0], tid);
   for (int c = 0; c < nchunks; ++c) {
     const int cnt = min(CH_F, L - c * CH_F);
     if (c + 1 < nchunks) {
-      stage_chunk<TMA>(buf[(c + 1) & 1], box[(c + 1) & 1], slab + 3 * (size_t)(c + 1) * CH_F,
-                       cull + (size_t)(c + 1) * CH_F, min(CH_F, L - (c + 1) * CH_F), &bar[(c + 1) & 1], tid);
+      stage_chunk<TMA>(S.buf[(c + 1) & 1], S.box[(c + 1) & 1], slab + 3 * (size_t)(c + 1) * CH_F,
+                       cull + (size_t)(c + 1) * CH_F, min(CH_F, L - (c + 1) * CH_F), &S.bar[(c + 1) & 1], tid);
       pending = c + 1;
     } else {
       pending = -1;
     }
-    if (TMA) mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
+    if (TMA) mbar_wait(&S.bar[c & 1], (uint32_t)((c >> 1) & 1));
     else __syncthreads();
-    if (!__all_sync(0xffffffffu, done)) {
-      const float4* rec = buf[c & 1];
-      const float4* bb = box[c & 1];
+    if (donemask != FULL) {
+      const float4* rec = S.buf[c & 1];
+      const float4* bb = S.box[c & 1];
       const int base = c * CH_F;
-      for (int g0 = 0; g0 < cnt; g0 += 32) {
+      for (int g0 = 0; g0 < cnt && donemask != FULL; g0 += 32) {
+        // ---- cull: one record per lane
         const int r = g0 + lane;
-        bool hit = false;
-        if (r < cnt) hit = box_hits(bb[r], wx0, wx1, wy0, wy1);
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-          const int j = g0 + __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float4 a = rec[3 * j], b = rec[3 * j + 1];
-          float dx, dy, G, alpha;
-          bool ok = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && !done;
-          const float test_T = T * (1.0f - alpha);
-          if (ok && test_T < T_STOP) { done = true; ok = false; }
-          const float Tb = T;
-          if (ok) {
-            const float4 cc = rec[3 * j + 2];
-            const float w = alpha * T;
-            C0 += b.z * w; C1 += b.w * w; C2 += cc.x * w; D += cc.y * w;
-            T = test_T;
-            last = base + j + 1;
-          }
-          if (LOG) {
-            const unsigned cb = __ballot_sync(0xffffffffu, ok);
-            if (cb) {
-              const int n = __popc(cb);
-              // a run (the pairs of one record) never straddles a 32-record boundary of the log: skip to the next
-              // boundary (one lane leaves a SKIP marker) so that the backward can walk the log in fixed 32-record
-              // batches with every run whole and every batch address known in advance
-              const int pos32 = (Cw - room) & 31;
-              if (pos32 + n > 32) {
-                const int pad = 32 - pos32;
-                if (lane == 0 && room > 0) plog[0].x = PAIR_SKIP;
-                plog += 2 * pad;
-                room -= pad;
-              }
-              room -= n;             // keeps counting past the capacity: reports the size that would have been needed
-              if (ok && room >= 0) {
-                uint4* dst = plog + 2 * __popc(cb & lt_mask);
-                dst[0] = make_uint4((unsigned)(base + j) | lane_bits, __float_as_uint(G), __float_as_uint(Tb), __float_as_uint(C0));
-                dst[1] = make_uint4(__float_as_uint(C1), __float_as_uint(C2), __float_as_uint(D), 0u);
-              }
-              plog += 2 * n;
-            }
+        int n = 0;
+        unsigned ent = 0u;
+        if (r < cnt) {
+          float fx0, fx1, fy0, fy1;
+          if (region_rect(bb[r], wx0, wx1, wy0, wy1, fx0, fx1, fy0, fy1)) {
+            const int ix0 = (int)fx0, iy0 = (int)fy0;
+            const int w = (int)fx1 - ix0 + 1, h = (int)fy1 - iy0 + 1;
+            n = w * h;
+            ent = (unsigned)r | ((unsigned)(ix0 - bx) << 8) | ((unsigned)(iy0 - by) << 11) | ((unsigned)(w - 1) << 13);
           }
         }
+        const unsigned nz = __ballot_sync(FULL, n > 0);
+        if (nz == 0u) continue;
+        const int incl = warp_incl_scan_i(n, lane);
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int excl = incl - n;
+        if (total >= DENSE_MIN * __popc(nz)) {
+          // ---- dense path: one touched record per iteration, lane = its own pixel
+          if (queued) drain();
+          unsigned mask = nz;
+          while (mask) {
+            const int jr = g0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 a = rec[3 * jr], b = rec[3 * jr + 1];
+            float dx, dy, G, alpha;
+            bool ok = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && !done;
+            const float test_T = T * (1.0f - alpha);
+            if (ok && test_T < T_STOP) { done = true; ok = false; }
+            if (ok) {
+              const float4 cc = rec[3 * jr + 2];
+              const float w = alpha * T;
+              C0 += b.z * w; C1 += b.w * w; C2 += cc.x * w; D += cc.y * w;
+              T = test_T;
+              last = base + jr + 1;
+            }
+            if (LOG) {
+              const unsigned cb = __ballot_sync(FULL, ok);
+              if (cb) {
+                const int off = npairs + __popc(cb & lt_mask);
+                if (ok && off < Cw) plog[off] = make_uint2((unsigned)(base + jr) | ((unsigned)lane << 25), __float_as_uint(G));
+                npairs += __popc(cb);
+              }
+            }
+          }
+          donemask = __ballot_sync(FULL, done);
+          continue;
+        }
+        // ---- sparse path: lane = candidate pair
+        if (n > 0) hits[__popc(nz & lt_mask)] = ent | ((unsigned)excl << 16);
+        __syncwarp();
+        int nbefore = 0;   // touched records that start before the current batch
+        for (int b0 = 0; b0 < total; b0 += 32) {
+          const int rel = excl - b0;
+          const unsigned heads = __reduce_or_sync(FULL, (n > 0 && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+          const int qi = b0 + lane;
+          const bool valid = qi < total;
+          const int rr = nbefore + __popc(heads & (FULL >> (31 - lane))) - 1;
+          nbefore += __popc(heads);
+          const unsigned he = hits[valid ? rr : 0];
+          const int jr = (int)(he & 255u);
+          const int w = (int)((he >> 13) & 7u) + 1;
+          const int k = qi - (int)(he >> 16);
+          const int row = (k >= w) + (k >= 2 * w) + (k >= 3 * w);
+          const int plx = (int)((he >> 8) & 7u) + (k - row * w), ply = (int)((he >> 11) & 3u) + row;
+          const int pl = (ply << 3) + plx;        // lane that owns the pixel
+          const float4 a = rec[3 * jr], b = rec[3 * jr + 1];
+          float dx, dy, G, alpha;
+          const bool ok = valid && eval_alpha(a, b, (float)(bx + plx), (float)(by + ply), dx, dy, G, alpha) &&
+                          !((donemask >> (pl & 31)) & 1u);
+          const unsigned cb = __ballot_sync(FULL, ok);
+          if (cb == 0u) continue;
+          unsigned peers = 0u;
+          int slot = 0, tot = 0;
+          if (ok) {
+            peers = __match_any_sync(cb, pl);
+            const int cntp = qc[pl];
+            slot = cntp + __popc(peers & lt_mask);
+            tot = cntp + __popc(peers);
+          }
+          if (__ballot_sync(FULL, ok && slot >= QD)) {     // a queue would overflow: composite what is queued first
+            drain();
+            slot = __popc(peers & lt_mask);
+            tot = __popc(peers);
+          }
+          for (;;) {
+            if (ok && slot >= 0 && slot < QD) q[slot * 32 + pl] = make_uint2(__float_as_uint(alpha), (unsigned)(base + jr));
+            if (ok && (peers >> lane) == 1u && tot > 0) qc[pl] = min(tot, QD);    // the pixel's last pair of the batch
+            const unsigned more = __ballot_sync(FULL, ok && slot >= QD);
+            __syncwarp();
+            queued = true;
+            if (more == 0u) break;
+            drain();                                       // > QD pairs of one pixel in one batch: go round again
+            slot -= QD;
+            tot -= QD;
+          }
+          if (LOG) {
+            const int off = npairs + __popc(cb & lt_mask);
+            if (ok && off < Cw) plog[off] = make_uint2((unsigned)(base + jr) | ((unsigned)pl << 25), __float_as_uint(G));
+            npairs += __popc(cb);
+          }
+        }
+        __syncwarp();      // hits[] is rewritten by the next cull group
       }
     }
     if (free_running) {
-      if (__all_sync(0xffffffffu, done)) break;
-    } else if (__syncthreads_and(done)) {
-      break;
+      if (donemask == FULL) break;
+    } else {
+      if (queued) drain();     // the queues point into the staged records, which the next chunk overwrites
+      if (__syncthreads_and(donemask == FULL)) break;
     }
   }
-  if (TMA && pending >= 0 && tid == 0) mbar_wait(&bar[pending & 1], (uint32_t)((pending >> 1) & 1));
+  if (queued) drain();
+  if (TMA && pending >= 0 && tid == 0) mbar_wait(&S.bar[pending & 1], (uint32_t)((pending >> 1) & 1));
   if (LOG) {
     if (lane == 0) {
-      const int npairs = Cw - room;
-      const bool okw = (room >= 0 && L <= (int)PAIR_J_MASK);
-      st.pair_count[(size_t)t * 8 + (tid >> 5)] = okw ? npairs : -1;
+      const bool okw = (npairs <= Cw && L <= (int)PAIR_J_MASK);
+      st.pair_count[(size_t)t * 8 + wid] = okw ? npairs : -1;
       if (!okw) st.control[3] = 1;
-      atomicMax(&blk_pairs, npairs);
+      atomicMax(&S.blk_pairs, npairs);
     }
     __syncthreads();
-    if (tid == 0 && blk_pairs > 0) atomicMax(st.control + 2, blk_pairs);
+    if (tid == 0 && S.blk_pairs > 0) atomicMax(st.control + 2, S.blk_pairs);
   }
 
   if (inside) {
@@ -223,18 +362,22 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   }
 }
 
+template <bool TMA, bool LOG>
+static cudaError_t launch_blend_forward_t(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
+                                          const SpfRasterOut& out, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(blend_forward_kernel<TMA, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(FwdSmem));
+  if (e != cudaSuccess) return e;
+  pdl_launch(blend_forward_kernel<TMA, LOG>, d.B * d.T, TILE_THREADS, sizeof(FwdSmem), s)(d, in.bg, st, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_blend_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                  const SpfRasterOut& out, cudaStream_t s) {
-  const int grid = d.B * d.T;
   const bool log = st.pair_log != nullptr && st.pair_count != nullptr && d.pair_cap > 0;
-  if (d.flags & SPF_FLAG_NO_TMA) {
-    if (log) pdl_launch(blend_forward_kernel<false, true>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
-    else pdl_launch(blend_forward_kernel<false, false>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
-  } else {
-    if (log) pdl_launch(blend_forward_kernel<true, true>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
-    else pdl_launch(blend_forward_kernel<true, false>, grid, TILE_THREADS, 0, s)(d, in.bg, st, out);
-  }
-  return cudaGetLastError();
+  if (d.flags & SPF_FLAG_NO_TMA)
+    return log ? launch_blend_forward_t<false, true>(d, in, st, out, s) : launch_blend_forward_t<false, false>(d, in, st, out, s);
+  return log ? launch_blend_forward_t<true, true>(d, in, st, out, s) : launch_blend_forward_t<true, false>(d, in, st, out, s);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -332,7 +475,7 @@ blend_backward_v1_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterStat
   for (int i = maxc * 10 + tid; i < L * 10; i += TILE_THREADS) {
     const int r = i / 10, k = i - r * 10;
     const int slot = __float_as_int(__ldg(reinterpret_cast<const float*>(slab + 3 * r + 2) + 2));
-    dup_grad[(size_t)slot * 12 + k] = 0.0f;
+    if ((int64_t)slot < d.cap) dup_grad[(size_t)slot * 12 + k] = 0.0f;
   }
   if (maxc == 0) return;
 
@@ -415,7 +558,7 @@ blend_backward_v1_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterStat
       for (int w = 0; w < 8; ++w)
         if ((hitmask[w] >> j) & 1ull) sum += part[w][j][k];
       const int slot = __float_as_int(reinterpret_cast<const float*>(rec + 3 * j + 2)[2]);
-      dup_grad[(size_t)slot * 12 + k] = sum;
+      if ((int64_t)slot < d.cap) dup_grad[(size_t)slot * 12 + k] = sum;
     }
     __syncthreads();
   }
@@ -459,7 +602,7 @@ struct BwdSmem {
 template <bool TMA>
 __device__ __forceinline__ void blend_backward_tile(const Dims& d, const float* __restrict__ bg_all, const SpfRasterState& st,
                                                     const SpfRasterGradOut& go, float* __restrict__ dup_grad, int use_log,
-                                                    BwdSmem& S, const int t) {
+                                                    BwdSmem& S, const int t, uint32_t& ph0, uint32_t& ph1) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int view = t / d.T, tile = t - view * d.T;
   const int s = st.tile_ranges[2 * (size_t)t], e = st.tile_ranges[2 * (size_t)t + 1];
@@ -480,10 +623,7 @@ __device__ __forceinline__ void blend_backward_tile(const Dims& d, const float* 
   const size_t hw = (size_t)d.H * d.W;
   const size_t pix = (size_t)py * d.W + px;
 
-  if (tid == 0) {
-    S.max_contrib = 0;
-    if (TMA) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
-  }
+  if (tid == 0) S.max_contrib = 0;
   __syncthreads();
 
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, gd = 0.f, qtot = 0.f;
@@ -517,7 +657,7 @@ __device__ __forceinline__ void blend_backward_tile(const Dims& d, const float* 
   for (int i = maxc * 10 + tid; i < L * 10; i += TILE_THREADS) {
     const int r = i / 10, k = i - r * 10;
     const int slot = __float_as_int(__ldg(reinterpret_cast<const float*>(slab + 3 * r + 2) + 2));
-    dup_grad[(size_t)slot * 12 + k] = 0.0f;
+    if ((int64_t)slot < d.cap) dup_grad[(size_t)slot * 12 + k] = 0.0f;
   }
   if (maxc == 0) return;
 
@@ -542,8 +682,13 @@ __device__ __forceinline__ void blend_backward_tile(const Dims& d, const float* 
       const int n4 = (cnt * 10 + 3) >> 2;
       for (int i = lane; i < n4; i += 32) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (TMA) mbar_wait(&S.bar[c & 1], (uint32_t)((c >> 1) & 1));
-    else __syncthreads();
+    if (TMA) {   // the two mbarriers live for the whole (persistent) kernel: every thread tracks their phase parity
+      uint32_t& ph = (c & 1) ? ph1 : ph0;
+      mbar_wait(&S.bar[c & 1], ph & 1u);
+      ++ph;
+    } else {
+      __syncthreads();
+    }
     __syncwarp();
 
     const float4* rec = S.rec[c & 1];
@@ -643,7 +788,7 @@ __device__ __forceinline__ void blend_backward_tile(const Dims& d, const float* 
 #pragma unroll
       for (int w = 0; w < 8; ++w) sum += S.part[w][j][k];
       const int slot = __float_as_int(reinterpret_cast<const float*>(rec + 3 * j + 2)[2]);
-      dup_grad[(size_t)slot * 12 + k] = sum;
+      if ((int64_t)slot < d.cap) dup_grad[(size_t)slot * 12 + k] = sum;
     }
     __syncthreads();
   }
@@ -660,35 +805,46 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
   const int n_tiles = d.B * d.T;
   if (use_log && st.control[3] == 0) return;     // every tile was handled from the pair log
+  if (TMA && threadIdx.x == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
+  uint32_t ph0 = 0u, ph1 = 0u;     // completed phases of the two mbarriers (initialised once, reused by every tile)
+  __syncthreads();
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    blend_backward_tile<TMA>(d, bg_all, st, go, dup_grad, use_log, S, t);
-    __syncthreads();     // shared memory (incl. the mbarriers, re-initialised per tile) is reused by the next tile
+    blend_backward_tile<TMA>(d, bg_all, st, go, dup_grad, use_log, S, t, ph0, ph1);
+    __syncthreads();     // shared memory is reused by the next tile
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Blend backward, v3: consumes the forward's pair log -- no alpha tests, no per-pixel sequential state.
+// Blend backward, v4: consumes the forward's 8-byte pair log -- no alpha tests, no per-pixel sequential pass.
 //
-// For a logged pair i of pixel p:  dL/dalpha_i = T_i q_i - (Qtot_p - g_p . S_i) / (1 - alpha_i), with S_i the blended
-// sums after the pair (logged), g_p = (dL/dC, dL/dD) and Qtot_p = g_p . S_final + T_final (bg . dL/dC - dL/dA).
-// Every pair is independent: warp w walks the log of forward-warp w 32 pairs at a time, ONE PAIR PER LANE (whole
-// runs only: a batch is cut at the last run boundary, so a Gaussian's pairs of this warp are always reduced in
-// one segmented shuffle reduction).  A Gaussian whose alpha box overlaps a single 8x4 warp region (the common case
-// with SPFSplatV2's ~2 px splats) is final after that reduction and its 10 sums are stored straight to its
-// duplicate slot; one that overlaps several regions parks its per-warp sums in shared-memory exchange slots that
-// are added in fixed region order after ONE block barrier.  No atomics on floats, fixed order: bit-reproducible.
-// Long tile lists are processed in windows of LOG_W records (each warp's log is sorted by record).  Tiles with an
-// incomplete log or too many multi-region records in a window are left to the recomputing kernel above (flagged
-// through pair_count).
+// For a logged pair i of pixel p:  dL/dalpha_i = T_i q_i - (Qtot_p - P_i) / (1 - alpha_i),  q_i = g_p . (rgb_i, depth_i),
+// g_p = (dL/dC, dL/dD), P_i = sum_{j<=i} q_j alpha_j T_j and Qtot_p = g_p . S_final + T_final (bg . dL/dC - dL/dA).
+// Warp w walks the log of forward-warp w 32 pairs at a time, ONE PAIR PER LANE.  T_i and P_i are not logged: they are
+// rebuilt by a KEYED SCAN -- the running (T, P) of the warp's 32 pixels live in shared memory; within a batch the pairs
+// of one pixel (match.any on the pixel lane; usually one, seldom more than three) are chained in log order, each taking
+// (T, P) from its predecessor with two shuffles; the last one writes the pixel's state back.  T_i is recomputed with the
+// forward's own operation (T <- T * (1 - alpha)) and is therefore bit-identical to the T the forward blended with.
+//
+// The pairs of a record (a "run": adjacent log entries, in pixel-lane order) are summed by a segmented shuffle
+// reduction; a run cut by a batch boundary parks its first part in shared memory and the next batch's lane 0 adds it.
+// A record whose alpha box overlaps a single 8x4 warp region (the common case with SPFSplatV2's ~2 px splats) is final
+// after that and its 10 sums are stored straight to its duplicate slot; one that overlaps several regions parks its
+// per-warp sums in exchange slots that are added in fixed region order after ONE block barrier.  No atomics on floats,
+// fixed order: bit-reproducible.  Long tile lists are processed in windows of LOG_W records (each warp's log is sorted
+// by record).  Tiles with an incomplete log or too many multi-region records in a window are left to the recomputing
+// kernel above (flagged through pair_count).
 constexpr int LOG_W = 416;         // records per window of the tile list (staged in shared memory)
 constexpr int LOG_ESLOTS = 640;    // exchange slots per window (one per (multi-region record, overlapped region))
 
 struct LogSmem {
   float4 rec[LOG_W * 3];                 // the window's slab records
-  float4 pg[TILE_THREADS];
-  float pq[TILE_THREADS];
+  float4 pg[TILE_THREADS];               // per pixel: dL/dC (3), dL/dD
+  float pq[TILE_THREADS];                // per pixel: Qtot
+  float Ts[TILE_THREADS], Ps[TILE_THREADS];   // per pixel: running transmittance and prefix P of the keyed scan
+  int nc[TILE_THREADS];                  // per pixel: n_contrib (pairs of later records are dead)
   uint32_t info[LOG_W];                  // region mask (8 bits) | first exchange slot << 8
   float exch[LOG_ESLOTS][10];
+  float carry[8][12];                    // per warp: sums of a run cut by the batch boundary
   uint32_t wrote[LOG_W / 32];
   int base;
 };
@@ -716,20 +872,21 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
   const int tx0 = (tile % d.gx) * TILE, ty0 = (tile / d.gx) * TILE;
   const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
   const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
-  const uint4* lp = reinterpret_cast<const uint4*>(st.pair_log) + ((size_t)t * 8 + wid) * (size_t)d.pair_cap * 2;
+  const uint2* lp = reinterpret_cast<const uint2*>(st.pair_log) + ((size_t)t * 8 + wid) * (size_t)d.pair_cap;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  // the log is read in fixed 32-record batches (runs never straddle a batch: the forward pads), so batch addresses do
-  // not depend on data: each batch is prefetched towards the SM three batches ahead and then loaded where it is
-  // used (ptxas does not keep register loads in flight across the loop back-edge, so a register pipeline would
-  // expose the full DRAM latency on every batch)
+  // the log is read in fixed 32-entry batches whose addresses do not depend on data: each batch is prefetched towards
+  // the SM three batches ahead and then loaded where it is used
   const int nbatch = (count + 31) >> 5;
   for (int k = 0; k < 3; ++k)
-    if ((k << 5) + lane < count) prefetch_l1(lp + 2 * (size_t)((k << 5) + lane));
+    if ((k << 5) + lane < count) prefetch_l1(lp + (size_t)((k << 5) + lane));
   int bi = 0;
+  int carry_j = -1;          // warp-uniform: record whose first part is parked in S.carry[wid]
 
-  // per-pixel upstream gradients and Qtot
+  // per-pixel upstream gradients, Qtot and scan state
   {
     float g0 = 0.f, g1 = 0.f, g2 = 0.f, gd = 0.f, qtot = 0.f;
+    int ncontrib = 0;
     if (inside) {
       float ga = 0.f;
       if (go.dL_dcolor) {
@@ -742,16 +899,24 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
       const float* bg = bg_all + view * 3;
       const float bgdot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2 - ga;
       qtot = (acc.x * g0 + acc.y * g1) + (acc.z * g2 + acc.w * gd) + st.final_T[(size_t)view * hw + pix] * bgdot;
+      ncontrib = st.n_contrib[(size_t)view * hw + pix];
     }
     S.pg[tid] = make_float4(g0, g1, g2, gd);
     S.pq[tid] = qtot;
+    S.Ts[tid] = 1.0f;
+    S.Ps[tid] = 0.0f;
+    S.nc[tid] = ncontrib;
   }
   const float4* pgw = S.pg + wid * 32;
   const float* pqw = S.pq + wid * 32;
+  float* Tw = S.Ts + wid * 32;
+  float* Pw = S.Ps + wid * 32;
+  const int* ncw = S.nc + wid * 32;
+  float* carry = S.carry[wid];
 
   for (int w0 = 0; w0 < L; w0 += LOG_W) {
     const int wn = min(LOG_W, L - w0), wend = w0 + wn;
-    // ---- window prologue: stage the records, region masks (the same box_hits test the forward used), exchange slots
+    // ---- window prologue: stage the records, region masks (the same rectangle test the forward used), exchange slots
     if (tid == 0) S.base = 0;
     for (int i = tid; i < LOG_W / 32; i += TILE_THREADS) S.wrote[i] = 0u;
     {
@@ -768,17 +933,19 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
         const float4 bb = __ldg(cull + w0 + r);
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
-          const float x0 = (float)(tx0 + (w & 1) * 8), y0 = (float)(ty0 + (w >> 1) * 4);
-          if (box_hits(bb, x0, x0 + 7.0f, y0, y0 + 3.0f)) mask |= 1u << w;
+          const int rx = tx0 + (w & 1) * 8, ry = ty0 + (w >> 1) * 4;
+          float f0, f1, f2, f3;
+          if (region_rect(bb, (float)rx, (float)min(rx + 7, d.W - 1), (float)ry, (float)min(ry + 3, d.H - 1), f0, f1, f2, f3))
+            mask |= 1u << w;
         }
       }
       const int nreg = __popc(mask);
       const int need = nreg > 1 ? nreg : 0;
       const int inc = warp_incl_scan_i(need, lane);
-      const int tot = __shfl_sync(0xffffffffu, inc, 31);
+      const int tot = __shfl_sync(FULL, inc, 31);
       int wbase = 0;
       if (lane == 0 && tot > 0) wbase = atomicAdd(&S.base, tot);   // slot POSITIONS may vary run to run; sums do not
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      wbase = __shfl_sync(FULL, wbase, 0);
       if (r < wn) S.info[r] = mask | ((unsigned)(wbase + inc - need) << 8);
     }
     __syncthreads();
@@ -790,65 +957,114 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
     // ---- this warp's pairs whose record lies in the window
     while (bi < nbatch) {
       const int idx = (bi << 5) + lane;
-      if (idx + 96 < count) prefetch_l1(lp + 2 * (size_t)(idx + 96));
-      uint4 e0 = make_uint4(PAIR_SKIP, 0u, 0u, 0u), e1 = e0;
-      if (idx < count) { e0 = lp[2 * (size_t)idx]; e1 = lp[2 * (size_t)idx + 1]; }
-      // lanes at / after a SKIP marker (or past the end of the log) hold no pair
-      const unsigned skipm = __ballot_sync(0xffffffffu, (idx >= count) || (e0.x == PAIR_SKIP));
-      const int nv = skipm ? __ffs(skipm) - 1 : 32;
-      const int jraw = (int)(e0.x & PAIR_J_MASK);
-      const bool act = (lane < nv) && (jraw >= w0) && (jraw < wend);
-      const bool beyond = (lane < nv) && (jraw >= wend);          // sorted by record: belongs to a later window
-      const unsigned bym = __ballot_sync(0xffffffffu, beyond);
-      int j = -1;
+      if (idx + 96 < count) prefetch_l1(lp + (size_t)(idx + 96));
+      const bool have = idx < count;
+      uint2 en = make_uint2(0u, 0u);
+      if (have) en = lp[idx];
+      const int jraw = have ? (int)(en.x & PAIR_J_MASK) : 0x7fffffff;
+      const int pl = (int)((en.x >> 25) & 31u);
+      const bool inwin = have && (jraw >= w0) && (jraw < wend);
+      const unsigned bym = __ballot_sync(FULL, have && (jraw >= wend));   // sorted by record: belongs to a later window
+      const int j = inwin ? jraw - w0 : -1;                               // run id (dead pairs stay part of their run)
+      const bool act = inwin && (jraw < ncw[pl]);
+      const unsigned am = __ballot_sync(FULL, act);
       float v[10];
 #pragma unroll
       for (int k = 0; k < 10; ++k) v[k] = 0.0f;
       int slot = 0;
-      if (act) {
-        j = jraw - w0;
-        const int pl = (int)((e0.x >> 25) & 31u);
-        const float G = __uint_as_float(e0.y), Tb = __uint_as_float(e0.z);
-        const float4 a = S.rec[3 * j], b = S.rec[3 * j + 1], cc = S.rec[3 * j + 2];
-        slot = __float_as_int(cc.z);
-        const float4 g = pgw[pl];
-        const float dx = a.x - (float)(bx + (pl & 7)), dy = a.y - (float)(by + (pl >> 3));
-        const float alpha = fminf(ALPHA_MAX, b.y * G);
-        const float qv = (b.z * g.x + b.w * g.y) + (cc.x * g.z + cc.y * g.w);
-        const float sg = (__uint_as_float(e0.w) * g.x + __uint_as_float(e1.x) * g.y) +
-                         (__uint_as_float(e1.y) * g.z + __uint_as_float(e1.z) * g.w);
-        const float dL_dalpha = Tb * qv - __fdividef(pqw[pl] - sg, 1.0f - alpha);
-        const float dL_dG = b.y * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
-        v[1] = dL_dG * (-gdy * b.x - gdx * a.w);
-        v[2] = -0.5f * gdx * dx * dL_dG;
-        v[3] = -gdx * dy * dL_dG;
-        v[4] = -0.5f * gdy * dy * dL_dG;
-        v[5] = G * dL_dalpha;
-        const float w = alpha * Tb;
-        v[6] = w * g.x; v[7] = w * g.y; v[8] = w * g.z; v[9] = w * g.w;
+      if (inwin) slot = __float_as_int(S.rec[3 * j + 2].z);
+      if (am) {
+        // keyed scan: (T_before, P_after) of every live pair
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, cc = a, g = a;
+        float G = 0.f, alpha = 0.f, qv = 0.f, c = 0.f, Tb = 1.0f, Pb = 0.0f;
+        unsigned peers = 0u;
+        int rank = 0, pp = lane;
+        if (act) {
+          G = __uint_as_float(en.y);
+          a = S.rec[3 * j]; b = S.rec[3 * j + 1]; cc = S.rec[3 * j + 2];
+          g = pgw[pl];
+          alpha = fminf(ALPHA_MAX, b.y * G);
+          qv = (b.z * g.x + b.w * g.y) + (cc.x * g.z + cc.y * g.w);
+          c = qv * alpha;
+          peers = __match_any_sync(am, pl);
+          const unsigned below = peers & lt_mask;
+          rank = __popc(below);
+          if (below) pp = 31 - __clz(below);
+          Tb = Tw[pl];
+          Pb = Pw[pl];
+        }
+        const int maxrank = __reduce_max_sync(FULL, rank);
+        float Ta = Tb * (1.0f - alpha), Pa = Pb + c * Tb;
+        for (int sidx = 1; sidx <= maxrank; ++sidx) {
+          const float Tn = __shfl_sync(FULL, Ta, pp), Pn = __shfl_sync(FULL, Pa, pp);
+          if (rank == sidx) {
+            Tb = Tn; Pb = Pn;
+            Ta = Tb * (1.0f - alpha); Pa = Pb + c * Tb;
+          }
+        }
+        if (act && (peers >> lane) == 1u) { Tw[pl] = Ta; Pw[pl] = Pa; }   // the pixel's last pair of the batch
+        __syncwarp();
+        if (act) {
+          const float dx = a.x - (float)(bx + (pl & 7)), dy = a.y - (float)(by + (pl >> 3));
+          const float dL_dalpha = Tb * qv - __fdividef(pqw[pl] - Pa, 1.0f - alpha);
+          const float dL_dG = b.y * dL_dalpha;
+          const float gdx = G * dx, gdy = G * dy;
+          v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
+          v[1] = dL_dG * (-gdy * b.x - gdx * a.w);
+          v[2] = -0.5f * gdx * dx * dL_dG;
+          v[3] = -gdx * dy * dL_dG;
+          v[4] = -0.5f * gdy * dy * dL_dG;
+          v[5] = G * dL_dalpha;
+          const float w = alpha * Tb;
+          v[6] = w * g.x; v[7] = w * g.y; v[8] = w * g.z; v[9] = w * g.w;
+        }
       }
+      // segmented reduction over runs of equal record
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
-        const int jo = __shfl_down_sync(0xffffffffu, j, off);
+        const int jo = __shfl_down_sync(FULL, j, off);
         const bool same = (lane + off < 32) && (jo == j) && (j >= 0);
-        if (!__any_sync(0xffffffffu, same)) break;
+        if (!__any_sync(FULL, same)) break;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
-          const float vo = __shfl_down_sync(0xffffffffu, v[k], off);
+          const float vo = __shfl_down_sync(FULL, v[k], off);
           if (same) v[k] += vo;
         }
       }
-      const int jprev = __shfl_up_sync(0xffffffffu, j, 1);
-      if (act && (lane == 0 || jprev != j)) {          // run head: holds this warp's sums for record j
+      const int jprev = __shfl_up_sync(FULL, j, 1);
+      const bool head = (j >= 0) && (lane == 0 || jprev != j);
+      if (carry_j >= 0) {                      // first part of lane 0's run, parked by the previous batch
+        if (lane == 0 && inwin && jraw == carry_j) {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) v[k] = carry[k] + v[k];
+        }
+        carry_j = -1;
+        __syncwarp();
+      }
+      // does the last run continue in the next batch?  (lane 31 peeks at the next entry)
+      int cont = 0;
+      if (lane == 31 && inwin && idx + 1 < count) cont = ((int)(lp[idx + 1].x & PAIR_J_MASK) == jraw) ? 1 : 0;
+      cont = __shfl_sync(FULL, cont, 31);
+      const unsigned hm = __ballot_sync(FULL, head);
+      const int hlast = hm ? 31 - __clz(hm) : -1;
+      if (cont) {
+        if (lane == hlast) {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) carry[k] = v[k];
+        }
+        carry_j = __shfl_sync(FULL, jraw, 31);
+        __syncwarp();
+      }
+      if (head && !(cont && lane == hlast)) {          // run head: holds this warp's sums for record j
         const unsigned info = S.info[j];
         const unsigned mask = info & 0xffu;
         if (__popc(mask) <= 1) {
-          float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-          *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+          if ((int64_t)slot < d.cap) {
+            float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+          }
           atomicOr(&S.wrote[j >> 5], 1u << (j & 31));
         } else {
           float* ex = S.exch[(info >> 8) + __popc(mask & ((1u << wid) - 1u))];
@@ -877,6 +1093,7 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
         continue;
       }
       const int slot = __float_as_int(reinterpret_cast<const float*>(&S.rec[3 * r + 2])[2]);
+      if ((int64_t)slot >= d.cap) continue;
       float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
       dst[0] = make_float4(v[0], v[1], v[2], v[3]);
       dst[1] = make_float4(v[4], v[5], v[6], v[7]);

@@ -105,8 +105,11 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
 #pragma unroll
     for (int k = 0; k < 10; ++k) a[k] = 0.0f;
     if (tiles > 0) {
+      // a replayed CUDA graph whose duplicate count outgrew the frozen capacity: never read past the buffer (the
+      // results of such a replay are invalid anyway and flagged through control[1])
+      const int ndup = (int)max((int64_t)0, min((int64_t)tiles, d.cap - (int64_t)off));
       const float4* rec = reinterpret_cast<const float4*>(gin.dup_grad) + 3 * (size_t)off;
-      for (int j = 0; j < tiles; ++j) {
+      for (int j = 0; j < ndup; ++j) {
         const float4 r0 = rec[3 * j], r1 = rec[3 * j + 1];
         const float2 r2 = *reinterpret_cast<const float2*>(rec + 3 * j + 2);
         a[0] += r0.x; a[1] += r0.y; a[2] += r0.z; a[3] += r0.w;
@@ -199,6 +202,9 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
     if (!use_sh && gin.dL_dcolors)
       for (int i = 0; i < 3; ++i) gin.dL_dcolors[sg * 3 + i] = dcol[i];
   }
+  // the bulk load must have landed before this CTA may exit or reuse the buffer, also when no thread consumed it
+  // (every Gaussian of the block culled in every view)
+  if (use_sh && tma && tid == 0) mbar_wait(&bar, 0);
   if (use_sh && gin.dL_dshs) {
     float* dst = gin.dL_dshs + row_off;
     if (tma) {

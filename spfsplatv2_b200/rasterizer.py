@@ -33,8 +33,9 @@ _ticket = [0]
 _pair_cap_hint: dict = {}
 _pair_stat: dict = {}         # key -> [[pinned int32[1], event, age in forwards], ...]
 _pin_pool: list = []          # recycled (pinned int32[1], event) pairs: cudaHostAlloc per step would cost ~100 us
-PAIR_CAP_DEFAULT = 512
-PAIR_LOG_BUDGET = 4 << 30     # bytes; above this the capacity is clipped and the densest tiles fall back to recomputation
+PAIR_CAP_DEFAULT = 512        # pairs per warp; the log holds 8 bytes per pair (4 KB per warp, 134 MB for 16 views at 256^2)
+PAIR_BYTES = 8
+PAIR_LOG_BUDGET = 2 << 30     # bytes; above this the capacity is clipped and the densest tiles fall back to recomputation
 
 
 def _ptr(t: Optional[Tensor]):
@@ -213,7 +214,7 @@ def _pair_capacity(key, n_warps: int) -> int:
             if need > cap:
                 cap = ((int(need * 1.25) + 63) // 64) * 64
                 _pair_cap_hint[key] = cap
-    return max(64, min(cap, (PAIR_LOG_BUDGET // (32 * max(n_warps, 1))) // 64 * 64))
+    return max(64, min(cap, (PAIR_LOG_BUDGET // (PAIR_BYTES * max(n_warps, 1))) // 64 * 64))
 
 
 def _launch_forward(st: "_State", fixed: _Workspace, cap: int, color, depth, alpha):
@@ -274,7 +275,7 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     if pair_log and s.pair_log:
         if capturing:
             pair_cap = max(64, min(int(_pair_cap_hint.get(key, PAIR_CAP_DEFAULT)),
-                                   (PAIR_LOG_BUDGET // (32 * max(B * T * 8, 1))) // 64 * 64))
+                                   (PAIR_LOG_BUDGET // (PAIR_BYTES * max(B * T * 8, 1))) // 64 * 64))
         else:
             pair_cap = _pair_capacity(key, B * T * 8)
     else:
@@ -293,7 +294,7 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
             ("tile_ranges", (B * T, 2), i32), ("final_T", (B, H, W), f32), ("n_contrib", (B, H, W), i32),
             ("accum", (B, H, W, 4), f32)]
     if pair_cap > 0:
-        spec += [("pair_log", (B * T * 8, pair_cap, 8), f32), ("pair_count", (B * T * 8,), i32)]
+        spec += [("pair_log", (B * T * 8, pair_cap, PAIR_BYTES // 4), f32), ("pair_count", (B * T * 8,), i32)]
     fixed = _Workspace(dev, spec)
     color = torch.empty(B, 3, H, W, dtype=f32, device=dev)
     depth = torch.empty(B, 1, H, W, dtype=f32, device=dev)

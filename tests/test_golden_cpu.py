@@ -119,3 +119,25 @@ def test_orthographic_glue_matches_reference():
     assert np.array_equal(tanfov[0].double().numpy(), g["rec_tanfov"])
     assert list(g["tanfov_types"]) == ["Tensor", "Tensor"]          # the shim must coerce tensors to floats
     assert np.array_equal(info["near"].numpy(), g["dump_near"]) and np.array_equal(info["far"].numpy(), g["dump_far"])
+
+
+def test_fullsize_fixture_c2p_reproduced_by_the_oracle():
+    """tests/golden/fullsize_c2p.npz (the headline 65k scene at 256x256) is what the oracle produces today on the seeded
+    scene: guards the fixture against drift of the oracle, of the scene generator and of torch's CPU RNG."""
+    import os
+    from tests.golden import fullsize as F
+    from tests.util import oracle_views
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_c2p.npz")
+    fx = np.load(p)
+    sc = F.scene_of("c2p")
+    assert F.inputs_digest(sc) == str(fx["inputs_sha"])
+    res, _ = oracle_views(sc, bg=F.CONFIGS["c2p"]["bg"])
+    r = res[0]
+    assert r["keys"].numel() == int(fx["n_dups"])
+    assert F.sha(r["keys"]) == str(fx["keys_sha"]) and F.sha(r["point_list"]) == str(fx["point_list_sha"])
+    assert torch.equal(r["n_contrib"], torch.from_numpy(fx["n_contrib"].astype(np.int32)))
+    assert torch.equal(r["color"], torch.from_numpy(fx["color"]))
+    for name in F.CONFIGS:      # every committed fixture belongs to the scene its config describes
+        q = os.path.join(os.path.dirname(p), f"fullsize_{name}.npz")
+        if os.path.exists(q):
+            assert F.inputs_digest(F.scene_of(name)) == str(np.load(q)["inputs_sha"]), name

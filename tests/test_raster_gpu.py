@@ -264,33 +264,35 @@ def test_pair_log_counts_and_capacity_feedback():
     assert need == int(counts.max()) and need > 64
     # total pairs == number of (pixel, Gaussian) contributions; cross-check against the oracle's blend weights
     ref, _ = oracle_views(sc)
-    # every logged pair carries its pixel's lane and a record index below that pixel's n_contrib
-    log = st.tensors["pair_log"].cpu().view(torch.int32).view(-1, 4096, 8)
+    # every logged pair carries its pixel's lane and its record's index in the tile list; pairs of one record are
+    # adjacent and in lane order; a pair is live iff its record index is below the pixel's n_contrib
+    log = st.tensors["pair_log"].cpu().view(torch.int32).view(-1, 4096, 2)
     nc = st.tensors["n_contrib"][0].cpu()
     assert torch.equal(nc, ref[0]["n_contrib"])
-    total = 0
+    lens = (st.tensors["tile_ranges"][:, 1] - st.tensors["tile_ranges"][:, 0]).cpu()
+    total = live = 0
+    per_pixel = torch.zeros(64, 64, dtype=torch.int64)
     for wi in range(counts.numel()):
         c = int(counts[wi])
         if c == 0:
             continue
         w0 = log[wi, :c, 0].to(torch.int64) & 0xFFFFFFFF
-        # runs never straddle a 32-record block: the rest of a block after a SKIP marker (0xffffffff) is padding
-        keep = torch.ones(c, dtype=torch.bool)
-        for blk in range(0, c, 32):
-            mk = (w0[blk:blk + 32] == 0xFFFFFFFF).nonzero()
-            if mk.numel():
-                keep[blk + int(mk[0]):blk + 32] = False
-        w0 = w0[keep]
-        c = int(keep.sum())
         j = w0 & ((1 << 25) - 1)
         lane = (w0 >> 25) & 31
         tile, wid = wi // 8, wi % 8
         px = (tile % 4) * 16 + (wid % 2) * 8 + (lane % 8)
         py = (tile // 4) * 16 + (wid // 2) * 4 + (lane // 8)
-        assert (j < nc[py, px].to(torch.int64)).all()
-        assert (j[1:] >= j[:-1]).all()                       # hit order
+        assert (j < int(lens[tile])).all()
+        assert (j[1:] >= j[:-1]).all()                                   # list order
+        same = j[1:] == j[:-1]
+        assert (lane[1:][same] > lane[:-1][same]).all()                  # lane order inside a run
+        alive = j < nc[py, px].to(torch.int64)
+        per_pixel.index_put_((py[alive], px[alive]), torch.ones(int(alive.sum()), dtype=torch.int64), accumulate=True)
         total += c
-    assert total > 0
+        live += int(alive.sum())
+    assert total > 0 and live > 0.9 * total
+    # a pixel with n_contrib > 0 has at least one live pair and vice versa
+    assert torch.equal(per_pixel > 0, nc > 0)
     R._pair_cap_hint[key] = 64
     st2 = forward_with_state(s, *args, pair_log=True)[4]
     c2 = st2.tensors["pair_count"].cpu()
