@@ -28,7 +28,6 @@
 
 namespace spf {
 
-constexpr int CH_F = 256;  // records per forward chunk  (12 KB slab + 4 KB boxes)
 constexpr int CH_B = 64;   // records per backward chunk
 
 __device__ __forceinline__ void warp_block_of_thread(int tid, int tile, int gx, int& bx, int& by) {
@@ -83,28 +82,30 @@ __device__ __forceinline__ bool region_rect(const float4& bb, float x0, float x1
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Blend forward, v4: PAIR-PARALLEL alpha evaluation, per-pixel queues for the (order-dependent) compositing.
+// Blend forward, v5: per-region HIT LISTS, PAIR-PARALLEL alpha evaluation, per-pixel queues for the compositing.
 //
 // With SPFSplatV2's splat sizes a warp region (8x4 pixels) is touched by ~57 records of a tile's ~370, and a touched
 // record covers ~5.6 of the region's 32 pixel centres, ~4.3 of which pass the alpha test (scripts/pair_stats.py).  The
-// previous kernel spent one 32-lane iteration per touched record at 4/32 useful lanes.  Here a warp works in two
-// alternating phases:
+// first-generation kernel spent one 32-lane iteration per touched record at 4/32 useful lanes, and every warp culled
+// the whole tile list by itself.  Here the tile list is processed in passes of PASS records (one TMA bulk copy):
 //
-//   phase A (lane = candidate (record, pixel) pair).  32 records are culled at a time, one per lane: the integer
-//       pixel rectangle of the record's alpha box inside the region (region_rect) gives n = w*h candidates; a warp
-//       scan of n and a bit mask of run heads (redux.or) let lane l of a batch find the record and the pixel of
-//       candidate number 32*batch + l.  Each lane evaluates ONE alpha; contributing pairs are appended, in
-//       (record, pixel) order, to the queue of their pixel (match.any ranks same-pixel pairs of a batch) and, if a
-//       backward follows, to the warp's pair log.
-//   phase B (lane = pixel).  Every pixel composites its queue front to back (T, colour, depth, early stop, last
-//       contributor) -- ~14 instructions per pair.  Queues are drained when one fills up, before the staged records
-//       they point to are recycled, and at the end of the list.
+//   cull (whole block, one record per thread): the integer pixel rectangle of the record's alpha box inside the tile
+//       is intersected with the eight 8x4 warp regions; every non-empty intersection becomes one HIT entry
+//       {record, first pixel lane, width-1, height-1} appended -- in list order (ballots + a prefix over the warps) --
+//       to that region's hit list in shared memory.  Every box is read once per tile, straight from global memory.
+//   phase A (per warp, lane = candidate (record, pixel) pair): 32 hits at a time live one per lane in registers; a
+//       warp scan of their pixel counts and a bit mask of run heads (redux.or) let lane l of a batch find the hit
+//       (one shuffle) and the pixel (a 256-byte lookup table) of candidate number 32*batch + l.  Each lane evaluates
+//       ONE alpha; contributing pairs are appended, in (record, pixel) order, to the queue of their pixel (match.any
+//       ranks same-pixel pairs of a batch) and, if a backward follows, to the warp's pair log.
+//   phase B (lane = pixel): every pixel composites its queue front to back (T, colour, depth, early stop, last
+//       contributor).  Queues are drained when one fills up and at the end of a pass.
 //
-// A cull group whose records cover most of the region (large splats: mean candidates per touched record >= DENSE_MIN)
-// takes the DENSE path instead -- one record per iteration, every lane evaluates its own pixel and composites at
-// once -- after the queues have been drained, so the per-pixel order is always the list order.  The arithmetic per
-// (pixel, record) is the same in both paths and the accept / reject decisions are the per-pixel tests of eval_alpha,
-// so images, final_T and n_contrib do not depend on the path taken.
+// A group of hits that covers most of the region (large splats: mean candidates per hit >= DENSE_MIN) takes the DENSE
+// path instead -- one record per iteration, every lane evaluates its own pixel and composites at once -- after the
+// queues have been drained, so the per-pixel order is always the list order; so does a region whose hit list
+// overflows.  The arithmetic per (pixel, record) is the same in all paths and the accept / reject decisions are the
+// per-pixel tests of eval_alpha, so images, final_T and n_contrib do not depend on the path taken.
 //
 // Pair log (LOG = true): one 8-byte entry per contributing pair, dense, in (record, pixel-lane) order:
 //   x = record index in the tile list | pixel lane << 25,  y = G = exp(power).
@@ -113,16 +114,21 @@ __device__ __forceinline__ bool region_rect(const float4& bb, float x0, float x1
 // writing and reports -1 (its tile is then handled by the recomputing backward).  control[2] = largest count needed.
 constexpr unsigned PAIR_J_MASK = (1u << 25) - 1u;
 constexpr int QD = 8;            // queue slots per pixel
-constexpr int DENSE_MIN = 12;    // mean candidates per touched record from which a cull group takes the dense path
+constexpr int DENSE_MIN = 12;    // mean candidates per hit from which a group of hits takes the dense path
+constexpr int PASS = 512;        // records per pass
+constexpr int HCAP = 256;        // hit entries per region and pass
 constexpr unsigned FULL = 0xffffffffu;
 
 struct FwdSmem {
-  float4 buf[2][CH_F * 3];       // staged slab records
-  float4 box[2][CH_F];           // staged alpha boxes
+  float4 buf[PASS * 3];          // the pass's slab records
+  uint32_t hit[8][HCAP];         // per region: record (9) | first pixel lane (5) << 9 | width-1 (3) << 14 | height-1 (2) << 17
   uint2 queue[8][QD * 32];       // per warp: [slot][pixel] = {alpha, record index in the tile list}
-  uint32_t hits[8][32];          // per warp: touched records of the current cull group (packed rectangle + prefix)
   int qcnt[8][32];               // per warp: queued pairs per pixel
-  uint64_t bar[2];
+  float2 pixf[8][32];            // per warp: pixel coordinates of the region's 32 pixel lanes
+  int wcnt[8][8], woff[8][8];    // [region][warp]: hits found by a warp in the current cull round / their offsets
+  int hbase[8];                  // per region: hits so far in this pass
+  uint8_t rowcol[8][32];         // [width-1][k] -> lane offset (row * 8 + column) of candidate k of a hit
+  uint64_t bar;
   int blk_pairs;
 };
 
@@ -142,20 +148,26 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   const int px = bx + (lane & 7), py = by + (lane >> 3);
   const bool inside = (px < d.W) && (py < d.H);
   const float pxf = (float)px, pyf = (float)py;
-  // the warp's region, clipped to the image (empty if the region lies outside: no candidates are ever generated)
+  const int tx0 = (tile % d.gx) * TILE, ty0 = (tile / d.gx) * TILE;
+  // the tile and the warp's region, clipped to the image
+  const float tx0f = (float)tx0, tx1f = (float)min(tx0 + TILE - 1, d.W - 1), ty0f = (float)ty0, ty1f = (float)min(ty0 + TILE - 1, d.H - 1);
   const float wx0 = (float)bx, wx1 = (float)min(bx + 7, d.W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, d.H - 1);
-  if (tid == 0) {
-    if (TMA) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
-    S.blk_pairs = 0;
-  }
   uint2* q = S.queue[wid];
   int* qc = S.qcnt[wid];
-  uint32_t* hits = S.hits[wid];
+  const uint32_t* hl = S.hit[wid];
+  if (tid == 0) {
+    if (TMA) { mbar_init(&S.bar, 1); mbar_fence_init(); }
+    S.blk_pairs = 0;
+  }
   qc[lane] = 0;
+  S.pixf[wid][lane] = make_float2(pxf, pyf);
+  {
+    const int w1 = wid, k = lane, w = w1 + 1;          // 256 threads = 8 widths x 32 candidates
+    S.rowcol[w1][k] = (uint8_t)(k < 4 * w ? (k / w) * 8 + (k % w) : 0);
+  }
   __syncthreads();
   const float4* slab = reinterpret_cast<const float4*>(st.slab) + 3 * (size_t)s;
   const float4* cull = reinterpret_cast<const float4*>(st.cullbox) + (size_t)s;
-  const int nchunks = (L + CH_F - 1) / CH_F;
   const int Cw = d.pair_cap;
   uint2* plog = LOG ? reinterpret_cast<uint2*>(st.pair_log) + ((size_t)t * 8 + wid) * (size_t)Cw : nullptr;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -166,29 +178,25 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   bool done = !inside;
   unsigned donemask = __ballot_sync(FULL, done);
   bool queued = false;   // warp-uniform: some queue is non-empty
-  int pending = -1;      // chunk whose TMA load is in flight beyond the current one
 
   // phase B: every pixel composites its queued pairs in list order
   auto drain = [&]() {
     const int n = qc[lane];
     const int maxn = __reduce_max_sync(FULL, n);
     for (int i = 0; i < maxn; ++i) {
-      if (i < n && !done) {
-        const uint2 en = q[i * 32 + lane];
-        const float alpha = __uint_as_float(en.x);
-        const unsigned idx = en.y;
-        const float test_T = T * (1.0f - alpha);
-        if (test_T < T_STOP) {
-          done = true;
-        } else {
-          const float4* r = S.buf[(idx / CH_F) & 1u] + 3u * (idx % CH_F);
-          const float2 c01 = *reinterpret_cast<const float2*>(&r[1].z);
-          const float2 c2d = *reinterpret_cast<const float2*>(&r[2].x);
-          const float w = alpha * T;
-          C0 += c01.x * w; C1 += c01.y * w; C2 += c2d.x * w; D += c2d.y * w;
-          T = test_T;
-          last = (int)idx + 1;
-        }
+      const uint2 en = q[i * 32 + lane];
+      const float alpha = __uint_as_float(en.x);
+      const float test_T = T * (1.0f - alpha);
+      const bool act = (i < n) && !done;
+      if (act && test_T < T_STOP) done = true;
+      if (act && !done) {
+        const float4* r = S.buf + 3u * (en.y & (unsigned)(PASS - 1));
+        const float2 c01 = *reinterpret_cast<const float2*>(&r[1].z);
+        const float2 c2d = *reinterpret_cast<const float2*>(&r[2].x);
+        const float w = alpha * T;
+        C0 += c01.x * w; C1 += c01.y * w; C2 += c2d.x * w; D += c2d.y * w;
+        T = test_T;
+        last = (int)en.y + 1;
       }
     }
     qc[lane] = 0;
@@ -196,99 +204,151 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
     donemask = __ballot_sync(FULL, done);
     __syncwarp();
   };
-
-  // Lists of at most two chunks (the common case) live entirely in the two buffers: nothing is ever refilled, so the
-  // warps need no block barrier at all -- each waits on the chunk's mbarrier and leaves as soon as ITS 32 pixels are
-  // done.  Longer lists recycle the buffers and keep the block in step.
-  const bool free_running = TMA && (nchunks <= 2);
-  if (nchunks > 0) stage_chunk<TMA>(S.buf[0], S.box[0], slab, cull, min(CH_F, L), &S.bar[0], tid);
-  for (int c = 0; c < nchunks; ++c) {
-    const int cnt = min(CH_F, L - c * CH_F);
-    if (c + 1 < nchunks) {
-      stage_chunk<TMA>(S.buf[(c + 1) & 1], S.box[(c + 1) & 1], slab + 3 * (size_t)(c + 1) * CH_F,
-                       cull + (size_t)(c + 1) * CH_F, min(CH_F, L - (c + 1) * CH_F), &S.bar[(c + 1) & 1], tid);
-      pending = c + 1;
-    } else {
-      pending = -1;
+  // dense step: every lane evaluates its own pixel against record jr of the pass and composites at once
+  auto dense_step = [&](int jr, int p0) {
+    const float4 a = S.buf[3 * jr], b = S.buf[3 * jr + 1];
+    float dx, dy, G, alpha;
+    bool ok = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && !done;
+    const float test_T = T * (1.0f - alpha);
+    if (ok && test_T < T_STOP) { done = true; ok = false; }
+    if (ok) {
+      const float4 cc = S.buf[3 * jr + 2];
+      const float w = alpha * T;
+      C0 += b.z * w; C1 += b.w * w; C2 += cc.x * w; D += cc.y * w;
+      T = test_T;
+      last = p0 + jr + 1;
     }
-    if (TMA) mbar_wait(&S.bar[c & 1], (uint32_t)((c >> 1) & 1));
-    else __syncthreads();
-    if (donemask != FULL) {
-      const float4* rec = S.buf[c & 1];
-      const float4* bb = S.box[c & 1];
-      const int base = c * CH_F;
-      for (int g0 = 0; g0 < cnt && donemask != FULL; g0 += 32) {
-        // ---- cull: one record per lane
-        const int r = g0 + lane;
-        int n = 0;
-        unsigned ent = 0u;
-        if (r < cnt) {
-          float fx0, fx1, fy0, fy1;
-          if (region_rect(bb[r], wx0, wx1, wy0, wy1, fx0, fx1, fy0, fy1)) {
-            const int ix0 = (int)fx0, iy0 = (int)fy0;
-            const int w = (int)fx1 - ix0 + 1, h = (int)fy1 - iy0 + 1;
-            n = w * h;
-            ent = (unsigned)r | ((unsigned)(ix0 - bx) << 8) | ((unsigned)(iy0 - by) << 11) | ((unsigned)(w - 1) << 13);
-          }
+    if (LOG) {
+      const unsigned cb = __ballot_sync(FULL, ok);
+      if (cb) {
+        const int off = npairs + __popc(cb & lt_mask);
+        if (ok && off < Cw) plog[off] = make_uint2((unsigned)(p0 + jr) | ((unsigned)lane << 25), __float_as_uint(G));
+        npairs += __popc(cb);
+      }
+    }
+  };
+
+  const int npass = (L + PASS - 1) / PASS;
+  for (int p = 0; p < npass; ++p) {
+    const int p0 = p * PASS, pc = min(PASS, L - p0);
+    // ---- stage the pass's records (one bulk copy) while the block culls
+    if (TMA) {
+      if (tid == 0) {
+        mbar_expect_tx(&S.bar, (uint32_t)pc * 48u);
+        tma_load_1d(S.buf, slab + 3 * (size_t)p0, (uint32_t)pc * 48u, &S.bar);
+      }
+    } else {
+      for (int i = tid; i < pc * 3; i += TILE_THREADS) S.buf[i] = slab[3 * (size_t)p0 + i];
+    }
+    // ---- cull: one record per thread, eight ordered per-region compactions (thread (w, wp) of the first 64 keeps
+    //      region w's running hit count and hands warp wp its offset)
+    int hrun = 0;
+    for (int r0 = 0; r0 < pc; r0 += TILE_THREADS) {
+      const int i = r0 + tid;
+      int X0 = 1, X1 = 0, Y0 = 1, Y1 = 0;      // tile-local pixel rectangle of the record's alpha box (empty)
+      if (i < pc) {
+        const float4 bb = __ldg(cull + p0 + i);
+        float f0, f1, f2, f3;
+        if (region_rect(bb, tx0f, tx1f, ty0f, ty1f, f0, f1, f2, f3)) {
+          X0 = (int)f0 - tx0; X1 = (int)f1 - tx0; Y0 = (int)f2 - ty0; Y1 = (int)f3 - ty0;
         }
-        const unsigned nz = __ballot_sync(FULL, n > 0);
-        if (nz == 0u) continue;
+      }
+      unsigned bal[8];
+      unsigned mask = 0u;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int hx = (w & 1) * 8, hy = (w >> 1) * 4;
+        const bool hit = (max(X0, hx) <= min(X1, hx + 7)) && (max(Y0, hy) <= min(Y1, hy + 3));
+        bal[w] = __ballot_sync(FULL, hit);
+        if (hit) mask |= 1u << w;
+        if (lane == w) S.wcnt[w][wid] = __popc(bal[w]);
+      }
+      __syncthreads();
+      if (tid < 64) {
+        const int w = tid >> 3, wp = tid & 7;
+        int off = hrun;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = S.wcnt[w][k];
+          if (k < wp) off += c;
+          hrun += c;
+        }
+        S.woff[w][wp] = off;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        if (mask & (1u << w)) {
+          const int hx = (w & 1) * 8, hy = (w >> 1) * 4;
+          const int xa = max(X0, hx), xb = min(X1, hx + 7), ya = max(Y0, hy), yb = min(Y1, hy + 3);
+          const int pos = S.woff[w][wid] + __popc(bal[w] & lt_mask);
+          if (pos < HCAP)
+            S.hit[w][pos] = (unsigned)i | ((unsigned)((ya - hy) * 8 + (xa - hx)) << 9) | ((unsigned)(xb - xa) << 14) |
+                            ((unsigned)(yb - ya) << 17);
+        }
+      }
+    }
+    if (tid < 64 && (tid & 7) == 0) S.hbase[tid >> 3] = hrun;
+    __syncthreads();               // hit lists and counts complete
+    if (TMA) mbar_wait(&S.bar, (uint32_t)(p & 1));
+    const int nh = S.hbase[wid];
+
+    if (donemask != FULL && nh > HCAP) {
+      // ---- the region's hit list overflowed (large splats): first-generation loop over the pass's records
+      if (queued) drain();
+      for (int g0 = 0; g0 < pc && donemask != FULL; g0 += 32) {
+        const int r = g0 + lane;
+        bool hit = false;
+        if (r < pc) {
+          float f0, f1, f2, f3;
+          hit = region_rect(__ldg(cull + p0 + r), wx0, wx1, wy0, wy1, f0, f1, f2, f3);
+        }
+        unsigned m = __ballot_sync(FULL, hit);
+        while (m) {
+          const int jr = g0 + __ffs(m) - 1;
+          m &= m - 1;
+          dense_step(jr, p0);
+        }
+        donemask = __ballot_sync(FULL, done);
+      }
+    } else if (donemask != FULL) {
+      for (int h0 = 0; h0 < nh && donemask != FULL; h0 += 32) {
+        // ---- 32 hits, one per lane
+        const int cnth = min(32, nh - h0);
+        unsigned he = 0u;
+        int n = 0;
+        if (lane < cnth) {
+          he = hl[h0 + lane];
+          n = (int)(((he >> 14) & 7u) + 1u) * (int)(((he >> 17) & 3u) + 1u);
+        }
         const int incl = warp_incl_scan_i(n, lane);
         const int total = __shfl_sync(FULL, incl, 31);
         const int excl = incl - n;
-        if (total >= DENSE_MIN * __popc(nz)) {
-          // ---- dense path: one touched record per iteration, lane = its own pixel
+        if (total >= DENSE_MIN * cnth) {
+          // ---- dense path: one hit per iteration, lane = its own pixel
           if (queued) drain();
-          unsigned mask = nz;
-          while (mask) {
-            const int jr = g0 + __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 a = rec[3 * jr], b = rec[3 * jr + 1];
-            float dx, dy, G, alpha;
-            bool ok = eval_alpha(a, b, pxf, pyf, dx, dy, G, alpha) && !done;
-            const float test_T = T * (1.0f - alpha);
-            if (ok && test_T < T_STOP) { done = true; ok = false; }
-            if (ok) {
-              const float4 cc = rec[3 * jr + 2];
-              const float w = alpha * T;
-              C0 += b.z * w; C1 += b.w * w; C2 += cc.x * w; D += cc.y * w;
-              T = test_T;
-              last = base + jr + 1;
-            }
-            if (LOG) {
-              const unsigned cb = __ballot_sync(FULL, ok);
-              if (cb) {
-                const int off = npairs + __popc(cb & lt_mask);
-                if (ok && off < Cw) plog[off] = make_uint2((unsigned)(base + jr) | ((unsigned)lane << 25), __float_as_uint(G));
-                npairs += __popc(cb);
-              }
-            }
-          }
+          for (int b = 0; b < cnth; ++b) dense_step((int)(__shfl_sync(FULL, he, b) & 511u), p0);
           donemask = __ballot_sync(FULL, done);
           continue;
         }
         // ---- sparse path: lane = candidate pair
-        if (n > 0) hits[__popc(nz & lt_mask)] = ent | ((unsigned)excl << 16);
-        __syncwarp();
-        int nbefore = 0;   // touched records that start before the current batch
+        he |= (unsigned)excl << 19;
+        int nbefore = 0;   // hits that start before the current batch
         for (int b0 = 0; b0 < total; b0 += 32) {
-          const int rel = excl - b0;
-          const unsigned heads = __reduce_or_sync(FULL, (n > 0 && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+          const unsigned rel = (unsigned)(excl - b0);
+          const unsigned heads = __reduce_or_sync(FULL, (n > 0 && rel < 32u) ? (1u << rel) : 0u);
           const int qi = b0 + lane;
           const bool valid = qi < total;
           const int rr = nbefore + __popc(heads & (FULL >> (31 - lane))) - 1;
           nbefore += __popc(heads);
-          const unsigned he = hits[valid ? rr : 0];
-          const int jr = (int)(he & 255u);
-          const int w = (int)((he >> 13) & 7u) + 1;
-          const int k = qi - (int)(he >> 16);
-          const int row = (k >= w) + (k >= 2 * w) + (k >= 3 * w);
-          const int plx = (int)((he >> 8) & 7u) + (k - row * w), ply = (int)((he >> 11) & 3u) + row;
-          const int pl = (ply << 3) + plx;        // lane that owns the pixel
-          const float4 a = rec[3 * jr], b = rec[3 * jr + 1];
+          const unsigned h = __shfl_sync(FULL, he, rr & 31);
+          const int jr = (int)(h & 511u);
+          const int k = (qi - (int)(h >> 19)) & 31;
+          const int pl = ((int)((h >> 9) & 31u) + (int)S.rowcol[(h >> 14) & 7u][k]) & 31;   // lane that owns the pixel
+          const float2 pf = S.pixf[wid][pl];
+          const float4 a = S.buf[3 * jr], b = S.buf[3 * jr + 1];
           float dx, dy, G, alpha;
-          const bool ok = valid && eval_alpha(a, b, (float)(bx + plx), (float)(by + ply), dx, dy, G, alpha) &&
-                          !((donemask >> (pl & 31)) & 1u);
+          const bool ok = eval_alpha(a, b, pf.x, pf.y, dx, dy, G, alpha) && valid && !((donemask >> pl) & 1u);
           const unsigned cb = __ballot_sync(FULL, ok);
           if (cb == 0u) continue;
           unsigned peers = 0u;
@@ -305,7 +365,7 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
             tot = __popc(peers);
           }
           for (;;) {
-            if (ok && slot >= 0 && slot < QD) q[slot * 32 + pl] = make_uint2(__float_as_uint(alpha), (unsigned)(base + jr));
+            if (ok && slot >= 0 && slot < QD) q[slot * 32 + pl] = make_uint2(__float_as_uint(alpha), (unsigned)(p0 + jr));
             if (ok && (peers >> lane) == 1u && tot > 0) qc[pl] = min(tot, QD);    // the pixel's last pair of the batch
             const unsigned more = __ballot_sync(FULL, ok && slot >= QD);
             __syncwarp();
@@ -317,22 +377,15 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
           }
           if (LOG) {
             const int off = npairs + __popc(cb & lt_mask);
-            if (ok && off < Cw) plog[off] = make_uint2((unsigned)(base + jr) | ((unsigned)pl << 25), __float_as_uint(G));
+            if (ok && off < Cw) plog[off] = make_uint2((unsigned)(p0 + jr) | ((unsigned)pl << 25), __float_as_uint(G));
             npairs += __popc(cb);
           }
         }
-        __syncwarp();      // hits[] is rewritten by the next cull group
       }
     }
-    if (free_running) {
-      if (donemask == FULL) break;
-    } else {
-      if (queued) drain();     // the queues point into the staged records, which the next chunk overwrites
-      if (__syncthreads_and(donemask == FULL)) break;
-    }
+    if (queued) drain();           // the queues point into the staged records, which the next pass overwrites
+    if (p + 1 < npass && __syncthreads_and(donemask == FULL)) break;
   }
-  if (queued) drain();
-  if (TMA && pending >= 0 && tid == 0) mbar_wait(&S.bar[pending & 1], (uint32_t)((pending >> 1) & 1));
   if (LOG) {
     if (lane == 0) {
       const bool okw = (npairs <= Cw && L <= (int)PAIR_J_MASK);
