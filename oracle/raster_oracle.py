@@ -120,9 +120,19 @@ def sh_basis(deg: int, d: Tensor) -> Tensor:
 
 def preprocess(means: Tensor, scales: Tensor, quats: Tensor, opacities: Tensor,
                shs: Optional[Tensor], colors: Optional[Tensor], view: View,
-               quat_order: str = "wxyz") -> dict:
+               quat_order: str = "wxyz", enable_cov_grad: bool = True,
+               enable_sh_grad: bool = True) -> dict:
     """Per-Gaussian projection.  fp32, fixed op
-    order.  Returns differentiable xy/depth/conic/rgb and integer radius/rect."""
+    order.  Returns differentiable xy/depth/conic/rgb and integer radius/rect.
+
+    ``enable_cov_grad=False`` / ``enable_sh_grad=False`` (the two switches of
+    GaussianRasterizationSettings, cuda_splatting.py:117-118; both True in
+    every shipped config, splatting_cuda.yaml:4-5) detach, respectively, the
+    camera-dependent factor T = W J of the 2-D covariance (no gradient from the
+    covariance to the mean and the pose; scales and rotations still receive
+    theirs through Sigma) and the view direction of the SH colour (no gradient
+    from the colour to the mean and the pose; the SH coefficients still receive
+    theirs).  Forward values are unchanged."""
     assert means.dtype in (torch.float32, torch.float64)   # float64 only as a truth check for the gradient tests
     V, Pm = view.viewmatrix, view.projmatrix
     mx, my, mz = means[:, 0], means[:, 1], means[:, 2]
@@ -169,6 +179,9 @@ def preprocess(means: Tensor, scales: Tensor, quats: Tensor, opacities: Tensor,
     J12 = -(fy * tyc) / tz2
     T0 = [J00 * V[i, 0] + J02 * V[i, 2] for i in range(3)]
     T1 = [J11 * V[i, 1] + J12 * V[i, 2] for i in range(3)]
+    if not enable_cov_grad:
+        T0 = [x.detach() for x in T0]
+        T1 = [x.detach() for x in T1]
     U0 = [(T0[0] * Sg[0][j] + T0[1] * Sg[1][j]) + T0[2] * Sg[2][j] for j in range(3)]
     U1 = [(T1[0] * Sg[0][j] + T1[1] * Sg[1][j]) + T1[2] * Sg[2][j] for j in range(3)]
     a = ((U0[0] * T0[0] + U0[1] * T0[1]) + U0[2] * T0[2]) + COV_DILATION
@@ -205,6 +218,8 @@ def preprocess(means: Tensor, scales: Tensor, quats: Tensor, opacities: Tensor,
                               for i in range(3)])
         d = means - campos[None, :]
         dn = d / torch.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])[:, None]
+        if not enable_sh_grad:
+            dn = dn.detach()
         basis = sh_basis(view.sh_degree, dn)                     # [P,K]
         K = basis.shape[1]
         rgb = (basis[:, :, None] * shs[:, :K, :]).sum(dim=1) + 0.5
@@ -328,9 +343,11 @@ def blend(pre: dict, point_list: Tensor, ranges: Tensor, view: View,
 
 
 def render(means, scales, quats, opacities, shs, colors, view: View,
-           quat_order: str = "wxyz", clamp_straight_through: bool = True) -> dict:
+           quat_order: str = "wxyz", clamp_straight_through: bool = True,
+           enable_cov_grad: bool = True, enable_sh_grad: bool = True) -> dict:
     """Full forward for one view.  Differentiable outputs: color, depth, alpha."""
-    pre = preprocess(means, scales, quats, opacities, shs, colors, view, quat_order)
+    pre = preprocess(means, scales, quats, opacities, shs, colors, view, quat_order,
+                     enable_cov_grad, enable_sh_grad)
     keys, point_list, ranges = bin_and_sort(pre, view)
     color, depth, alpha, final_T, n_contrib = blend(pre, point_list, ranges, view,
                                                     clamp_straight_through)

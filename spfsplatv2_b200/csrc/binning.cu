@@ -22,7 +22,8 @@ namespace spf {
 
 // ---- K2: two independent exclusive scans in one launch (block 0 / block 1) ---------------------
 __device__ void block_exclusive_scan(const int* __restrict__ in, int* __restrict__ out, int64_t n,
-                                     int* total_out, volatile int* host_counters, int ticket) {
+                                     int* total_out, volatile int* host_counters, int ticket, int64_t capacity = 0,
+                                     int* overflow_out = nullptr) {
   __shared__ int warp_part[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -58,7 +59,10 @@ __device__ void block_exclusive_scan(const int* __restrict__ in, int* __restrict
   }
   if (tid == 0) {
     out[n] = carry_s;
-    if (total_out) *total_out = carry_s;
+    if (total_out) {
+      *total_out = carry_s;
+      if ((int64_t)carry_s > capacity) *overflow_out = 1;     // read by the blend kernel, which poisons the image
+    }
     if (host_counters) {        // mapped pinned host memory: N, fence, ticket
       host_counters[0] = carry_s;
       __threadfence_system();
@@ -69,9 +73,10 @@ __device__ void block_exclusive_scan(const int* __restrict__ in, int* __restrict
 
 __global__ void __launch_bounds__(1024)
 scan_kernel(const int* block_sum, int* block_off, int64_t n_blocks, const int* tile_count,
-            int* tile_start, int64_t n_tiles, int* n_total, int* host_counters, int ticket) {
+            int* tile_start, int64_t n_tiles, int* n_total, int* host_counters, int ticket, int64_t capacity,
+            int* overflow) {
   pdl_enter();
-  if (blockIdx.x == 0) block_exclusive_scan(block_sum, block_off, n_blocks, n_total, host_counters, ticket);
+  if (blockIdx.x == 0) block_exclusive_scan(block_sum, block_off, n_blocks, n_total, host_counters, ticket, capacity, overflow);
   else block_exclusive_scan(tile_count, tile_start, n_tiles, nullptr, nullptr, 0);
 }
 
@@ -79,7 +84,7 @@ cudaError_t launch_scan(const Dims& d, const SpfRasterState& st, const ControlLa
   int* c = st.control;
   pdl_launch(scan_kernel, 2, 1024, 0, s)(c + cl.block_sum, c + cl.block_off, (int64_t)d.B * d.NB, c + cl.tile_count,
                                  c + cl.tile_start, (int64_t)d.B * d.T, c + cl.n_total, st.host_counters,
-                                 d.ticket);
+                                 d.ticket, d.cap, c + cl.overflow);
   return cudaGetLastError();
 }
 

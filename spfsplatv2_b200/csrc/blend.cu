@@ -402,11 +402,15 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
     const size_t hw = (size_t)d.H * d.W;
     const size_t pix = (size_t)py * d.W + px;
     float* col = out.color + (size_t)view * 3 * hw;
-    col[pix] = C0 + T * bg[0];
-    col[hw + pix] = C1 + T * bg[1];
-    col[2 * hw + pix] = C2 + T * bg[2];
-    out.depth[(size_t)view * hw + pix] = D;
-    if (out.alpha) out.alpha[(size_t)view * hw + pix] = 1.0f - T;
+    // Duplicate buffer overflow (control[1]: more (Gaussian, tile) duplicates than dup_capacity; the excess was dropped):
+    // the image would silently miss Gaussians, so it is poisoned instead -- a loss computed from it is NaN, never a
+    // plausible wrong number -- until the caller has re-run the forward with the capacity control[0] asks for.
+    const float poison = st.control[1] != 0 ? __int_as_float(0x7fc00000) : 0.0f;
+    col[pix] = C0 + T * bg[0] + poison;
+    col[hw + pix] = C1 + T * bg[1] + poison;
+    col[2 * hw + pix] = C2 + T * bg[2] + poison;
+    out.depth[(size_t)view * hw + pix] = D + poison;
+    if (out.alpha) out.alpha[(size_t)view * hw + pix] = 1.0f - T + poison;
     st.final_T[(size_t)view * hw + pix] = T;
     st.n_contrib[(size_t)view * hw + pix] = last;
     // private copy of the blended sums (no background term): backward derives every pixel's total

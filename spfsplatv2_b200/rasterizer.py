@@ -10,6 +10,10 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import threading
+import time
+import weakref
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Optional
 
@@ -24,14 +28,32 @@ PROJ_THREADS = 128
 # Duplicate-buffer capacity policy: no device->host wait before the kernels are enqueued.  The buffers
 # are sized from a per-shape high-water mark; the exact count N comes back through pinned memory while
 # the blend kernel is already running, and the forward is re-run (rare) if N exceeded the capacity.
-_capacity_hint: dict = {}
+class DuplicateCapacityError(RuntimeError):
+    """A forward whose duplicate count was checked late (training call) had more (Gaussian, tile) duplicates than the
+    buffers sized from earlier calls of the shape.  Its image was poisoned with NaN by the blend kernel (never a
+    plausible wrong picture); the capacity has been raised: run the step again."""
+
+
+class _Hints(OrderedDict):
+    """Per-shape sizing hints: bounded (least recently used shape evicted) and guarded by the module lock."""
+    MAX = 64
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        self.move_to_end(key)
+        while len(self) > self.MAX:
+            self.popitem(last=False)
+
+
+_lock = threading.RLock()       # guards the sizing hints, the ticket counter and the pinned pools (host-side state only)
+_capacity_hint: dict = _Hints()
 GROWTH = 1.5
 _host_counters: dict = {}     # device index -> (pinned int32[2] tensor, numpy view)
 _ticket = [0]
 # Pair-log sizing (records per warp): per-shape high-water mark of control[2], fed back asynchronously after each
 # backward (pinned copy + event, polled -- never waited on -- by the next forward of that shape).
-_pair_cap_hint: dict = {}
-_pair_stat: dict = {}         # key -> [[pinned int32[1], event, age in forwards], ...]
+_pair_cap_hint: dict = _Hints()
+_pair_stat: dict = _Hints()         # key -> [[pinned int32[1], event, age in forwards], ...]
 _pin_pool: list = []          # recycled (pinned int32[1], event) pairs: cudaHostAlloc per step would cost ~100 us
 PAIR_CAP_DEFAULT = 512        # pairs per warp; the log holds 8 bytes per pair (4 KB per warp, 134 MB for 16 views at 256^2)
 PAIR_BYTES = 8
@@ -166,7 +188,7 @@ def _counters(dev):
 class _State:
     """Forward intermediates kept for backward / inspection (not autograd-tracked)."""
     __slots__ = ("desc", "cin", "cstate", "cout", "keep", "_n_dups", "capacity", "tensors", "key", "ticket", "slot",
-                 "dev", "settings", "scratch", "captured")
+                 "dev", "settings", "scratch", "captured", "__weakref__")
 
     @property
     def n_dups(self) -> int:
@@ -177,20 +199,37 @@ class _State:
         return self._n_dups
 
 
+def _poll_count(dev, slot, ticket):
+    """Non-blocking: the duplicate count of forward `ticket` if the scan kernel has already reported it, else None."""
+    _, host_np = _counters(dev)
+    if int(host_np[slot, 1]) == ticket:
+        return int(host_np[slot, 0])
+    return None
+
+
 def _wait_count(dev, slot, ticket, tensors) -> int:
+    """Waits for the scan kernel of forward `ticket` to report N through the pinned slot: a short busy poll (the usual
+    wait is a few microseconds), then sleeps of growing length so a long queue ahead of the kernel does not burn a core."""
     _, host_np = _counters(dev)
     spins = 0
+    t0 = None
     while True:
         cur = int(host_np[slot, 1])
         if cur == ticket:
             return int(host_np[slot, 0])
         if cur > ticket and (cur - ticket) % N_COUNTER_SLOTS == 0:
-            return int(tensors["control"][0])      # slot recycled by a later forward: ask the device (rare)
+            # slot recycled by a later forward: ask the device (rare)
+            return None if tensors is None else int(tensors["control"][0])
         spins += 1
-        if spins > 2_000_000 and (spins & 0xfffff) == 0:
-            torch.cuda.current_stream(dev).synchronize()   # surfaces a launch failure instead of hanging
-            if int(host_np[slot, 1]) != ticket and spins > 20_000_000:
-                raise RuntimeError("spf_raster_forward: duplicate count never arrived (kernel failure?)")
+        if spins > 2000:
+            if t0 is None:
+                t0 = time.monotonic()
+            waited = time.monotonic() - t0
+            time.sleep(min(1e-3, 2e-5 * (1 + (spins - 2000) // 50)))
+            if waited > 2.0:
+                torch.cuda.current_stream(dev).synchronize()   # surfaces a launch failure instead of hanging
+                if int(host_np[slot, 1]) != ticket:
+                    raise RuntimeError("spf_raster_forward: duplicate count never arrived (kernel failure?)")
 
 
 PAIR_FEEDBACK_LAG = 2   # forwards between a backward's report and its use
@@ -217,6 +256,29 @@ def _pair_capacity(key, n_warps: int) -> int:
     return max(64, min(cap, (PAIR_LOG_BUDGET // (PAIR_BYTES * max(n_warps, 1))) // 64 * 64))
 
 
+_unverified: dict = _Hints()     # key -> state of the last forward whose duplicate count has not been looked at yet
+
+
+def _check_unverified(key):
+    """A training-mode forward whose count was deferred and whose backward never ran (evaluation under enable_grad,
+    a discarded pose-search step): look at its count now -- it has long landed -- so that an overflow is reported
+    (and the capacity raised) instead of going unnoticed.  Holds (device, slot, ticket, capacity) only, never the
+    forward's buffers."""
+    prev = _unverified.pop(key, None)
+    if prev is None:
+        return
+    dev, slot, ticket, capacity = prev
+    n = _wait_count(dev, slot, ticket, None)
+    if n is None:          # the pinned slot was recycled by 16 later forwards: nothing left to look at
+        return
+    with _lock:
+        _capacity_hint[key] = max(int(_capacity_hint.get(key, 0)), int(n * GROWTH) + 1024)
+    if n > capacity:
+        raise DuplicateCapacityError(
+            f"spfsplatv2_b200: the previous forward of this shape had {n} tile duplicates for a buffer capacity of "
+            f"{capacity}; its image was NaN-poisoned.  The capacity has been raised: run it again.")
+
+
 def _launch_forward(st: "_State", fixed: _Workspace, cap: int, color, depth, alpha):
     """(Re)allocate the capacity-dependent buffers for `cap` duplicates and enqueue the whole forward sequence."""
     lib = L.lib()
@@ -225,8 +287,9 @@ def _launch_forward(st: "_State", fixed: _Workspace, cap: int, color, depth, alp
                              ("cullbox", (cap, 4), torch.float32)])
     st.tensors = _Tensors(fixed, capws)
     host_t, _ = _counters(dev)
-    _ticket[0] = (_ticket[0] % 0x3fffffff) + 1
-    st.ticket = _ticket[0]
+    with _lock:
+        _ticket[0] = (_ticket[0] % 0x3fffffff) + 1
+        st.ticket = _ticket[0]
     st.slot = st.ticket % N_COUNTER_SLOTS
     st.desc.dup_capacity = cap
     st.desc.ticket = st.ticket
@@ -236,8 +299,9 @@ def _launch_forward(st: "_State", fixed: _Workspace, cap: int, color, depth, alp
     st.cstate = L.SpfRasterState(*ptrs, None if getattr(st, "captured", False)
                                  else C.c_void_p(host_t.data_ptr() + 8 * st.slot))
     st.cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
-    L.check(lib.spf_raster_forward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(st.cout),
-                                   _stream(dev)), "spf_raster_forward")
+    with torch.cuda.device(dev):       # the C entry points launch on the CURRENT device's context
+        L.check(lib.spf_raster_forward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(st.cout),
+                                       _stream(dev)), "spf_raster_forward")
 
 
 def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg,
@@ -262,12 +326,14 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
 
     f32, i32 = torch.float32, torch.int32
     key = (dev.index, S, v, P, H, W)
+    capturing = torch.cuda.is_current_stream_capturing()
+    if not capturing:
+        _check_unverified(key)
     hint = _capacity_hint.get(key)
     cap = max(int(hint if hint is not None else 2 * B * P), 1024)
     # CUDA-graph capture (torch.cuda.graph around a whole fwd+loss+bwd step): nothing here may wait on the GPU, and the
     # sizes are frozen into the graph.  Run at least one eager step of the same shape first (it establishes the
     # capacities); afterwards `graph_overflowed(state)` tells whether a replay ever outgrew them.
-    capturing = torch.cuda.is_current_stream_capturing()
     if capturing and hint is None:
         raise RuntimeError("spfsplatv2_b200: run one eager forward of this shape before capturing it in a CUDA graph "
                            "(the duplicate-buffer capacity is learned from it)")
@@ -300,20 +366,31 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     depth = torch.empty(B, 1, H, W, dtype=f32, device=dev)
     alpha = torch.empty(B, 1, H, W, dtype=f32, device=dev) if s.want_alpha else None
     _launch_forward(st, fixed, cap, color, depth, alpha)
+    _last_state[0] = weakref.ref(st)
     if capturing:
         st._n_dups = cap            # sizes frozen at capture time
-    elif defer_count and hint is not None and not s.sync_count:
+        return color, depth, alpha, fixed["radii"], st
+    n = None
+    if defer_count and hint is not None and not s.sync_count:
         # Steady-state training call: the duplicate count is NOT awaited here (that would make the host wait for the
         # GPU to reach this call's scan kernel on every step).  Capacity = GROWTH x the largest count seen so far for
-        # this shape; the count is verified when the backward starts (see _Rasterize.backward).
-        pass
-    else:
-        while True:
+        # this shape.  If the count has already landed it is checked now (and the forward re-run if needed); otherwise
+        # it is verified when the backward starts (see _Rasterize.backward) or by the next forward of the shape.  A
+        # forward that did overflow never yields a plausible image: the blend kernel poisons it with NaN.
+        n = _poll_count(dev, st.slot, st.ticket)
+        if n is None:
+            _unverified[key] = (dev, st.slot, st.ticket, cap)
+            return color, depth, alpha, fixed["radii"], st
+    while True:
+        if n is None:
             n = st.n_dups        # polls the pinned slot: the rest of the forward is already queued behind the scan
-            if n <= cap:
-                break
-            cap = int(n * 1.05) + 1024
-            _launch_forward(st, fixed, cap, color, depth, alpha)
+        st._n_dups = n
+        if n <= cap:
+            break
+        cap = int(n * 1.05) + 1024
+        _launch_forward(st, fixed, cap, color, depth, alpha)
+        n = None
+    with _lock:
         _capacity_hint[key] = max(int(_capacity_hint.get(key, 0)), int(n * GROWTH) + 1024)
     return color, depth, alpha, fixed["radii"], st
 
@@ -348,21 +425,19 @@ class _Rasterize(torch.autograd.Function):
         B = S * s.views_per_scene
         NB = (P + PROJ_THREADS - 1) // PROJ_THREADS
         f32 = dict(dtype=torch.float32, device=dev)
-        # deferred duplicate-count check (the forward did not wait for it)
+        # deferred duplicate-count check (the forward did not wait for it; by now the count has long landed)
         n = st.n_dups
-        if (not st.captured) and n > st.capacity:
-            import warnings
-            warnings.warn(f"spfsplatv2_b200: {n} tile duplicates exceeded the buffer capacity {st.capacity} chosen from "
-                          "earlier calls; the forward image of this call dropped some Gaussians.  Re-running the forward "
-                          "with the exact size for the backward (capacity raised for later calls).")
-            B_, H_, W_ = st.desc.n_scenes * st.desc.views_per_scene, st.desc.image_height, st.desc.image_width
-            scratch = (torch.empty(B_, 3, H_, W_, **f32), torch.empty(B_, 1, H_, W_, **f32),
-                       torch.empty(B_, 1, H_, W_, **f32) if s.want_alpha else None)
-            st.scratch = scratch
-            _launch_forward(st, st.tensors.spaces[0], int(n * 1.05) + 1024, *scratch)
-            n = st.n_dups
+        pend = _unverified.get(st.key)
+        if pend is not None and pend[2] == st.ticket:
+            _unverified.pop(st.key, None)
         if not st.captured:
-            _capacity_hint[st.key] = max(int(_capacity_hint.get(st.key, 0)), int(n * GROWTH) + 1024)
+            with _lock:
+                _capacity_hint[st.key] = max(int(_capacity_hint.get(st.key, 0)), int(n * GROWTH) + 1024)
+            if n > st.capacity:
+                raise DuplicateCapacityError(
+                    f"spfsplatv2_b200: {n} tile duplicates exceeded the buffer capacity {st.capacity} chosen from earlier "
+                    "calls of this shape; the forward image of this step was NaN-poisoned (so was any loss computed from "
+                    "it).  The capacity has been raised: run the step again.")
         gc = None if g_color is None else _f32c(g_color)
         gd = None if g_depth is None else _f32c(g_depth)
         ga = None if (g_alpha is None or not s.want_alpha) else _f32c(g_alpha)
@@ -378,8 +453,9 @@ class _Rasterize(torch.autograd.Function):
         d_m2d = torch.empty(B, P, 3, **f32) if (s.want_means2d_grad and ctx.shapes[7] is not None) else None
         gin = L.SpfRasterGradIn(scratch.ptr("dup_grad"), scratch.ptr("pose_partial"), _ptr(d_means), _ptr(d_scales),
                                 _ptr(d_rots), _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
-        L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
-                                        C.byref(gin), _stream(dev)), "spf_raster_backward")
+        with torch.cuda.device(dev):
+            L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
+                                            C.byref(gin), _stream(dev)), "spf_raster_backward")
         if st.desc.pair_capacity > 0 and not st.captured and len(_pair_stat.setdefault(st.key, [])) < 4:
             # feed the largest per-warp pair count back to the sizing of the next forward (no wait)
             pin, ev = _pin_pool.pop() if _pin_pool else (torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
@@ -393,9 +469,20 @@ class _Rasterize(torch.autograd.Function):
                 None if d_m2d is None else d_m2d.view(sh[7]))
 
 
+_last_state = [None]
+
+
+def last_forward_state():
+    """State of the most recent forward issued by this process (None once it has been garbage-collected): lets a caller
+    of the autograd entry points reach `graph_overflowed` for a step captured in a CUDA graph."""
+    ref = _last_state[0]
+    return None if ref is None else ref()
+
+
 def graph_overflowed(st: "_State") -> bool:
-    """After replaying a captured step: did any replay outgrow the duplicate buffer frozen into the graph (results of
-    that replay are then invalid: re-capture after an eager step), and how the pair log fared.  Synchronises."""
+    """After replaying a captured step: did the LAST replay outgrow the duplicate buffer frozen into the graph?  Its
+    image (and any loss computed from it) is then NaN -- the blend kernel poisons it -- its gradients are invalid, and
+    nothing was written out of bounds: re-capture after an eager step of the denser scene.  Synchronises."""
     ctrl = st.tensors["control"][:4].cpu()
     return bool(int(ctrl[0]) > st.capacity or int(ctrl[1]) != 0)
 

@@ -184,6 +184,45 @@ def test_gradients_match_oracle_autograd(regime, h, w, grid, b, v):
     assert e < GRAD_TOL, f"extrinsics (pose): rel err {e:.3e}"
 
 
+@pytest.mark.parametrize("cov,sh,xyzw", [(False, True, False), (True, False, False), (False, False, False), (True, True, True)])
+def test_gradient_switches_and_quaternion_order(cov, sh, xyzw):
+    """GaussianRasterizationSettings.enable_cov_grad / enable_sh_grad = False (cuda_splatting.py:117-118,
+    config/model/decoder/splatting_cuda.yaml:4-5) in the BACKWARD, against the oracle with the corresponding factors
+    detached; and rotations given as (x,y,z,w) (SPF_FLAG_QUAT_XYZW), forward and backward."""
+    from spfsplatv2_b200.camera import camera_setup
+    from spfsplatv2_b200.rasterizer import RasterSettings, rasterize_batched
+    d = _dev()
+    b, v, h, w = 1, 2, 80, 64
+    sc = make_batch(b, seed=71, v_cxt=1, h=h, w=w, grid=(40, 40), regime="trained", n_target=v, with_cov=True)
+    bg = (0.2, 0.1, 0.4)
+    ref, leaves = oracle_views(sc, bg=bg, requires_grad=True, enable_cov_grad=cov, enable_sh_grad=sh,
+                               quat_order="xyzw" if xyzw else "wxyz")
+    torch.manual_seed(1)
+    wc = torch.randn(b * v, 3, h, w)
+    wd = 0.05 * torch.randn(b * v, 1, h, w)
+    loss = sum((r["color"] * wc[i]).sum() + (r["depth"] * wd[i]).sum() for i, r in enumerate(ref))
+    loss.backward()
+    ext = sc.extrinsics.clone().requires_grad_()
+    view, proj, tanfov, scale = camera_setup(ext.reshape(b * v, 4, 4), sc.intrinsics.reshape(b * v, 3, 3),
+                                             sc.near.reshape(-1), sc.far.reshape(-1), True)
+    t = {k: getattr(sc, k).to(d).requires_grad_() for k in ("means", "rotations", "scales", "harmonics", "opacities")}
+    s = RasterSettings(h, w, 4, 1.0, v, sh_layout_ck=True, enable_cov_grad=cov, enable_sh_grad=sh, quat_xyzw=xyzw)
+    bgt = torch.tensor(bg, dtype=torch.float32, device=d).expand(b * v, 3)
+    color, depth, _, _ = rasterize_batched(s, t["means"], t["scales"], t["rotations"], t["opacities"], t["harmonics"], None,
+                                           view.to(d), proj.to(d), tanfov.to(d), bgt, scale.to(d))
+    for i, r in enumerate(ref):
+        assert (color[i].cpu() - r["color"]).abs().max().item() < 3e-5
+    ((color * wc.to(d)).sum() + (depth * wd.to(d)).sum()).backward()
+    for name in ("means", "scales", "rotations", "opacities", "harmonics"):
+        e = rel_err(t[name].grad.cpu(), leaves[name].grad)
+        assert e < GRAD_TOL, f"{name}: rel err {e:.3e}"
+    assert rel_err(ext.grad, leaves["extrinsics"].grad) < GRAD_TOL
+    if not cov or not sh:      # the switches do change the gradient: the full gradient must NOT match
+        ref2, leaves2 = oracle_views(sc, bg=bg, requires_grad=True)
+        sum((r["color"] * wc[i]).sum() + (r["depth"] * wd[i]).sum() for i, r in enumerate(ref2)).backward()
+        assert rel_err(t["means"].grad.cpu(), leaves2["means"].grad) > 10 * GRAD_TOL
+
+
 def test_decoder_gradients_end_to_end():
     """Whole public path (DecoderSplattingCUDA with the fused GPU camera-setup kernel).  The GPU matrix inverse
     differs from the CPU one by ulps, which may flip individual alpha-threshold memberships (see above), so the
@@ -356,6 +395,107 @@ def test_capacity_overflow_reruns():
     assert a[4].n_dups > 1024
     b = _state_forward(sc)
     assert torch.equal(a[0], b[0]) and b[4].n_dups == a[4].n_dups
+
+
+def _train_call(sc, view, proj, tanfov, scale, d):
+    from spfsplatv2_b200.rasterizer import RasterSettings, rasterize_batched
+    h, w = sc.image_shape
+    t = {k: getattr(sc, k).to(d).requires_grad_() for k in ("means", "scales", "rotations", "opacities", "harmonics")}
+    s = RasterSettings(h, w, 4, 1.0, 1, sh_layout_ck=True)
+    color, depth, _, _ = rasterize_batched(s, t["means"], t["scales"], t["rotations"], t["opacities"], t["harmonics"], None,
+                                           view, proj, tanfov, torch.zeros(1, 3, device=d), scale)
+    return color, t
+
+
+def test_training_overflow_is_never_silent(monkeypatch):
+    """A training-mode forward sizes its duplicate buffers from earlier calls and does not wait for the count.  When the
+    count jumps past the capacity (here: the hint is cut to half of what the scene needs) the image must be either
+    correct (count already known: re-run inside the forward) or NaN-poisoned with the backward raising -- never a
+    plausible picture with Gaussians missing; the step after the error is correct again."""
+    from spfsplatv2_b200 import rasterizer as R
+    from spfsplatv2_b200.camera import camera_setup
+    d = _dev()
+    sc = make_scene(seed=61, v_cxt=1, h=64, w=64, grid=(40, 40), regime="trained", n_target=1)
+    view, proj, tanfov, scale = [x.to(d) for x in camera_setup(sc.extrinsics[0], sc.intrinsics[0], sc.near[0], sc.far[0], True)]
+    key = (0, 1, 1, sc.means.shape[1], 64, 64)
+    R._capacity_hint.clear(); R._unverified.clear()
+    ref, t = _train_call(sc, view, proj, tanfov, scale, d)          # first call of the shape: exact
+    n = R.last_forward_state().n_dups                               # (the state lives as long as the autograd graph)
+    ref = ref.detach().clone()
+    # (a) the count is already there when the forward looks: re-run inside the forward, image correct
+    R._capacity_hint[key] = n // 2
+    torch.cuda.synchronize()
+    color, t = _train_call(sc, view, proj, tanfov, scale, d)
+    torch.cuda.synchronize()
+    if torch.isnan(color).any():        # the poll came too early on this run: must then behave like (b)
+        with pytest.raises(R.DuplicateCapacityError):
+            color.sum().backward()
+    else:
+        assert torch.equal(color.detach(), ref)
+        color.sum().backward()
+    # (b) the count is NOT there yet (forced): poisoned image, the backward raises, the retry is correct
+    R._capacity_hint[key] = n // 2
+    monkeypatch.setattr(R, "_poll_count", lambda *a: None)
+    color, t = _train_call(sc, view, proj, tanfov, scale, d)
+    assert bool(torch.isnan(color).all())
+    with pytest.raises(R.DuplicateCapacityError):
+        color.sum().backward()
+    color, t = _train_call(sc, view, proj, tanfov, scale, d)
+    assert torch.equal(color.detach(), ref)
+    color.sum().backward()
+    assert all(torch.isfinite(x.grad).all() for x in t.values())
+    # (c) no backward ever follows the overflowed forward: the next forward of the shape reports it, the one after works
+    R._capacity_hint[key] = n // 2
+    color, t = _train_call(sc, view, proj, tanfov, scale, d)
+    assert bool(torch.isnan(color).all())
+    del color, t
+    with pytest.raises(R.DuplicateCapacityError):
+        _train_call(sc, view, proj, tanfov, scale, d)
+    color, t = _train_call(sc, view, proj, tanfov, scale, d)
+    assert torch.equal(color.detach(), ref)
+    R._capacity_hint.clear(); R._unverified.clear()
+
+
+def test_graph_replay_with_a_denser_scene_is_safe_and_flagged():
+    """A captured step freezes the duplicate capacity.  Replaying it on a denser scene (scales x4 in place: far more
+    tile duplicates than the capacity) must not write out of bounds (backward stores and reads are clipped to the
+    capacity; run under compute-sanitizer in profiles/), yields a NaN loss and sets the overflow flag; restoring the
+    scene and replaying reproduces the original loss bit for bit."""
+    from spfsplatv2_b200 import rasterizer as R
+    from spfsplatv2_b200.camera import camera_setup
+    from spfsplatv2_b200.rasterizer import RasterSettings, rasterize_batched
+    d = _dev()
+    sc = make_scene(seed=67, v_cxt=1, h=64, w=64, grid=(40, 40), regime="trained", n_target=1)
+    view, proj, tanfov, scale = [x.to(d) for x in camera_setup(sc.extrinsics[0], sc.intrinsics[0], sc.near[0], sc.far[0], True)]
+    R._capacity_hint.clear(); R._pair_cap_hint.clear(); R._pair_stat.clear(); R._unverified.clear()
+    stat = {k: getattr(sc, k).to(d) for k in ("means", "scales", "rotations", "opacities", "harmonics")}
+    s = RasterSettings(64, 64, 4, 1.0, 1, sh_layout_ck=True)
+    bg = torch.zeros(1, 3, device=d)
+
+    def step():
+        t = {k: v.detach().requires_grad_() for k, v in stat.items()}
+        color, depth, _, _ = rasterize_batched(s, t["means"], t["scales"], t["rotations"], t["opacities"], t["harmonics"], None,
+                                               view, proj, tanfov, bg, scale)
+        loss = color.square().mean()
+        loss.backward()
+        return loss, t
+    for _ in range(4):
+        loss_e, _ = step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_g, t_g = step()
+        st = R.last_forward_state()
+    graph.replay(); torch.cuda.synchronize()
+    assert torch.equal(loss_g, loss_e.detach()) and not R.graph_overflowed(st)
+    small = stat["scales"].clone()
+    stat["scales"].mul_(4.0)                       # in place: the graph reads the same memory
+    graph.replay(); torch.cuda.synchronize()
+    assert R.graph_overflowed(st) and bool(torch.isnan(loss_g))
+    stat["scales"].copy_(small)
+    graph.replay(); torch.cuda.synchronize()
+    assert not R.graph_overflowed(st) and torch.equal(loss_g, loss_e.detach())
+    assert all(torch.isfinite(x.grad).all() for x in t_g.values())
 
 
 def test_shim_matches_batched_path():

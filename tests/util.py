@@ -5,7 +5,8 @@ from oracle import raster_oracle as O
 from spfsplatv2_b200.camera import camera_setup
 
 
-def oracle_views(sc, scale_invariant=True, bg=(0.0, 0.0, 0.0), requires_grad=False, use_sh=True, dtype=torch.float32):
+def oracle_views(sc, scale_invariant=True, bg=(0.0, 0.0, 0.0), requires_grad=False, use_sh=True, dtype=torch.float32,
+                 **render_kw):
     """Render every (scene, view) of ``sc`` with the oracle.  Returns (list of per-view result
     dicts in (b v) order, leaves dict) -- leaves are CPU tensors with requires_grad for autograd."""
     b, v = sc.extrinsics.shape[:2]
@@ -26,7 +27,7 @@ def oracle_views(sc, scale_invariant=True, bg=(0.0, 0.0, 0.0), requires_grad=Fal
                     view[i].contiguous(), proj[i].contiguous(), int(sc.harmonics.shape[-1] ** 0.5 + 0.5) - 1, 1.0)
         shs = leaves["harmonics"][s].permute(0, 2, 1).contiguous()
         res = O.render(leaves["means"][s] * scale[i], leaves["scales"][s] * scale[i], leaves["rotations"][s],
-                       leaves["opacities"][s], shs if use_sh else None, None if use_sh else shs[:, 0, :], vw)
+                       leaves["opacities"][s], shs if use_sh else None, None if use_sh else shs[:, 0, :], vw, **render_kw)
         out.append(res)
     return out, leaves
 
