@@ -166,15 +166,49 @@ def run_ours(args):
     # On NVSwitch boxes the bucket is symmetric memory reduced in the switch by csrc/allreduce.cu (NVLS multimem);
     # elsewhere (or with SPF_ALLREDUCE=nccl) it is a plain tensor reduced by NCCL.
     reducer = GradAllReduce(dev) if world > 1 else None
-    ar_buf = reducer.alloc(16 * 1024 * 1024) if world > 1 else None
-    ar_backend = ("nvls" if reducer.uses_nvls(ar_buf) else "nccl") if world > 1 else None
+    # two buckets, alternating: step k's gradient lands in bucket k % 2 while the reduction of step k-1 may still run
+    ar_bufs = [reducer.alloc(16 * 1024 * 1024) for _ in range(2)] if world > 1 else None
+    ar_backend = ("nvls" if reducer.uses_nvls(ar_bufs[0]) else "nccl") if world > 1 else None
     if world > 1 and rank == 0 and reducer.nvls_error:
-        print(f"bench.py: NVLS all-reduce unavailable ({reducer.nvls_error}); using NCCL", file=sys.stderr)
+        print(f"bench.py: NVLS all-reduce: {reducer.nvls_error}", file=sys.stderr)
+    ar_done = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
+    ar_state = {"k": 0, "dep": "lag1"}
+    if world > 1:
+        for ev in ar_done:
+            ev.record(torch.cuda.current_stream(dev))
+
+    def ar_begin():
+        """Dependency a training loop imposes: step k may start once the gradient all-reduce of step k-1 has finished
+        (its sums feed the optimizer step k's forward reads; one step of slack = the usual pipelined / delayed-update
+        form).  dep == "none" drops it (the reduction is then never on the critical path)."""
+        if world > 1 and ar_state["dep"] == "lag1":
+            torch.cuda.current_stream(dev).wait_event(ar_done[(ar_state["k"] + 1) % 2])
+
+    def ar_launch():
+        """The step's replicated-parameter gradient: every rank writes rank+1 into the bucket (stand-in for the
+        backward's stores), then ONE sum all-reduce on the side stream.  Checked after the timed loop."""
+        if world == 1:
+            return
+        k = ar_state["k"]
+        buf = ar_bufs[k % 2]
+        buf.fill_(float(rank + 1))
+        reducer.launch([buf])
+        ar_done[k % 2].record(reducer.stream)
+        ar_state["k"] = k + 1
+
+    def ar_check():
+        reducer.wait()
+        torch.cuda.synchronize(dev)
+        want = float(world * (world + 1) // 2)
+        for i, buf in enumerate(ar_bufs):
+            if ar_state["k"] > i and not bool((buf == want).all()):
+                raise RuntimeError(f"gradient all-reduce gave wrong sums in bucket {i}: expected {want} everywhere, "
+                                   f"got min {float(buf.min())} max {float(buf.max())}")
 
     def step_resident():
+        ar_begin()
         loss, leaves, ext = _step(dec, Gaussians, dev_in)
-        if world > 1:
-            reducer.launch([ar_buf])
+        ar_launch()
         return loss
 
     # end-to-end: every step's inputs come from pinned host memory.  Double-buffered: step k+1's inputs cross PCIe on a
@@ -203,10 +237,10 @@ def run_ours(args):
         cur.wait_event(copied[k % 2])
         d = dict(e2e_bufs[k % 2])
         d["cov"], d["shape"] = dev_in["cov"], (h, w)
+        ar_begin()
         loss, leaves, ext = _step(dec, Gaussians, d)
         done[k % 2].record(cur)
-        if world > 1:
-            reducer.launch([ar_buf])
+        ar_launch()
         _prefetch((k + 1) % 2)                    # next step's host->device copy overlaps this step's kernels
         e2e_state["k"] = k + 1
         return float(loss.item())                 # device->host read of the step's result
@@ -255,9 +289,9 @@ def run_ours(args):
                 raise RuntimeError(f"graph replay loss {float(static_loss)} != eager loss {eager_val}")
 
             def step_resident():       # noqa: F811
+                ar_begin()
                 graph.replay()
-                if world > 1:
-                    reducer.launch([ar_buf])
+                ar_launch()
                 return static_loss
             graphed = True
         except Exception as exc:        # keep the eager loop
@@ -272,7 +306,18 @@ def run_ours(args):
     ms, wall = timed(step_resident, args.steps, args.warmup)
     if rank == 0:
         sampler.mark(time.time() - wall / 1e3, time.time())
+    last_loss = float(step_resident())
+    if not (last_loss == last_loss):       # NaN: a replay outgrew the duplicate buffers frozen into the graph (poisoned image)
+        raise RuntimeError("bench.py: the timed loop produced a NaN loss (duplicate-buffer overflow inside the captured graph)")
+    ms_nodep = None
+    if world > 1:
+        ar_check()                         # the reductions of the timed loop really summed every rank's bucket
+        ar_state["dep"] = "none"
+        ms_nodep, _ = timed(step_resident, args.steps, 3)
+        ar_state["dep"] = "lag1"
     ms_e2e, wall_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    if world > 1:
+        ar_check()
     clocks = sampler.stop() if rank == 0 else None
 
     views_total = b * world
@@ -317,7 +362,10 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "views_per_step_per_gpu": b, "gaussians_per_scene": P,
                        "duplicates_per_step": N, "image": [h, w], "sh_degree": 4,
-                       "parallelism": f"dp{world} (scenes sharded over ranks; 64 MiB stand-in grad all-reduce/step, {ar_backend})" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} (scenes sharded over ranks; one 64 MiB gradient-bucket sum all-reduce per step on a side stream, "
+                                       f"{ar_backend}{' + in-kernel barriers' if ar_backend == 'nvls' and reducer.fused_barrier else ''}; step k waits for the "
+                                       f"reduction of step k-1; sums verified after the timed loop)") if world > 1 else "single GPU",
+                       "value_without_allreduce_dependency": round(views_total * args.steps / (ms_nodep / 1e3), 2) if ms_nodep else None,
                        "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step > 126 MB L2, no explicit flush",
                        "loop": "one CUDA graph per step (fwd + fused MSE + bwd)" if graphed else "eager PyTorch loop",
                        "loss": "fused MSE (spfsplatv2_b200.loss.mse_loss)",
@@ -337,12 +385,69 @@ def run_ours(args):
                               "frac": round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
             "wall_ms_per_step": round(wall / args.steps, 4),
         }
+        if world == 1 and not args.no_rope:
+            line["roofline_rope"] = rope_bench(dev, peaks["hbm_gbs"])
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, sample_views=args.cpu_views)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+ROPE_SHAPES = {   # (B, N, H, D): q / k of the fused qkv tensor as the attention blocks pass them (croco/blocks.py:97-104)
+    "encoder": (48, 256, 16, 64),     # ViT-L encoder, 16 heads x 64, 16x16 patches of a 256x256 view, 48 views per step
+    "decoder": (16, 258, 12, 64),     # decoder blocks, 12 heads x 64, 256 patch tokens + 2 extra tokens
+}
+
+
+def rope_bench(dev, hbm_gbs: float, iters: int = 20) -> dict:
+    """2-D RoPE (north_star: curope/kernels.cu:17-108) on SPFSplatV2's q/k shapes: q and k of a fused qkv tensor rotated in
+    place by ONE launch (spf_rope2d_qk).  Device time from CUDA events around a replayed CUDA graph that cycles through
+    enough distinct qkv buffers to exceed L2 (no cache reuse between timed launches); the eager figure adds the Python
+    + ctypes call path.  Algorithmic bytes per launch = 2 tensors x 2 x B*N*H*D*sizeof + 16*B*N (positions)."""
+    from spfsplatv2_b200.curope import rope_2d_qk
+    out = {}
+    for name, (B, N, H, D) in ROPE_SHAPES.items():
+        for dt_name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+            esz = torch.empty(0, dtype=dt).element_size()
+            qkv_bytes = B * N * 3 * H * D * esz
+            nbuf = max(2, -(-300_000_000 // qkv_bytes))
+            bufs = [torch.randn(B, N, 3, H, D, device=dev, dtype=dt) for _ in range(nbuf)]
+            pos = torch.randint(0, 16, (B, N, 2), device=dev, dtype=torch.int64)
+            views = [(b[:, :, 0], b[:, :, 1]) for b in bufs]
+
+            def cycle():
+                for q, k in views:
+                    rope_2d_qk(q, k, pos, 100.0, 1.0)
+            for _ in range(3):
+                cycle()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                cycle()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            eager_us = e0.elapsed_time(e1) * 1e3 / (iters * nbuf)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                cycle()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(iters):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / (iters * nbuf)
+            algo = 2 * 2 * B * N * H * D * esz + 16 * B * N
+            gbs = algo / (us * 1e-6) / 1e9
+            out[f"{name}_{dt_name}"] = {"shape": [B, N, H, D], "us_per_qk_launch": round(us, 2), "us_per_qk_launch_eager": round(eager_us, 2),
+                                        "achieved": round(gbs, 1), "frac": round(gbs / hbm_gbs, 4), "bytes": algo, "buffers_cycled": nbuf}
+            del bufs, views, graph
+    return {"bound": "hbm", "unit": "GB/s", "peak": hbm_gbs, "kernel": "rope2d_kernel (q and k in one launch)", "cases": out}
 
 
 def cpu_baseline(workload: str, sample_views: int = 3) -> dict:
@@ -365,10 +470,68 @@ def cpu_baseline(workload: str, sample_views: int = 3) -> dict:
             "sample": f"{sample_views} views of workload {workload} (fwd+bwd, torch CPU, {cores} threads)"}
 
 
+def _reference_cuda_arm(args, mod):
+    """The REAL reference rasterizer (diff_gauss_pose) on the GPU, driven per view like cuda_splatting.py:96-143
+    (tests/ref_probe.reference_render_loop), same workload and metric as our arm; value = views/s device-timed, e2e = the
+    same loop fed from pinned host memory."""
+    from spfsplatv2_b200.loss import mse_loss
+    from tests.ref_probe import reference_render_loop
+    v_cxt, h, w, b, desc = WORKLOADS[args.workload]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    sc, host = _make_inputs(args.workload, 0, pin=True)
+    names = ("means", "scales", "rotations", "opacities", "harmonics", "extrinsics")
+
+    def step(src):
+        leaves = {k: src[k].detach().requires_grad_() for k in names}
+        scd = sc.__class__(leaves["means"], None, leaves["rotations"], leaves["scales"], leaves["harmonics"], leaves["opacities"],
+                           leaves["extrinsics"], src["intrinsics"], src["near"], src["far"], (h, w))
+        color, _ = reference_render_loop(mod, scd, torch.zeros(b, 3, device=dev), leaves=leaves)
+        loss = ((color - src["gt"][:, 0]) ** 2).mean()
+        loss.backward()
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    dev_in = {k: v.to(dev) for k, v in host.items()}
+    ms = timed(lambda: step(dev_in), args.steps, max(3, args.warmup))
+    ms_e2e = timed(lambda: float(step({k: v.to(dev, non_blocking=True) for k, v in host.items()})), args.steps, 3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    value, e2e = b * args.steps / (ms / 1e3), b * args.steps / (ms_e2e / 1e3)
+    return {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "gaussians_per_scene": sc.means.shape[1], "image": [h, w], "sh_degree": 4,
+                       "note": f"REAL reference rasterizer {getattr(mod, '__file__', '?')} through the reference's per-view loop"},
+            "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": 0, "kind": "reference-cuda",
+                             "sample": f"{b} views per step, {args.steps} steps, on the GPU"},
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the real reference rasterizer, if this box has one (site-packages or baseline/_ref); else its CPU restatement
+    from tests.ref_probe import find_reference_rasterizer
+    mod, why = find_reference_rasterizer()
+    if mod is not None and torch.cuda.is_available():
+        try:
+            print(json.dumps(_reference_cuda_arm(args, mod)), flush=True)
+            return
+        except Exception as exc:
+            why = f"diff_gauss_pose found but its run failed ({type(exc).__name__}: {exc})"
+    print(f"bench.py --impl reference: {why}; timing the CPU oracle port instead", file=sys.stderr)
     v_cxt, h, w, b, desc = WORKLOADS[args.workload]
     from spfsplatv2_b200.synthetic import make_scene
     from tests.util import oracle_views
@@ -398,7 +561,7 @@ def run_reference(args):
             "ms_per_step": round(1e3 * sum(times) / n, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "gaussians_per_scene": P, "image": [h, w], "sh_degree": 4,
-                       "note": "reference CUDA rasterizer diff_gauss_pose is not vendored/installable; this is the CPU oracle port"},
+                       "note": f"reference CUDA rasterizer unavailable ({why}); this is the CPU oracle port"},
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"1 view per step, {n} steps, torch CPU {cores} threads"},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -414,6 +577,7 @@ def main():
     ap.add_argument("--workload", default="c2p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager PyTorch loop instead of a captured CUDA graph")
+    ap.add_argument("--no-rope", action="store_true", help="skip the RoPE roofline block of the N=1 line")
     ap.add_argument("--cpu-views", type=int, default=4)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -213,10 +213,19 @@ SPF_API int spf_adapter_backward(const float* raw, const float* dL_dscales, cons
 
 /* 2-D RoPE, in place.  Replaces rope_2d (curope.cpp:49-65).  tokens: [B,N,H,D] view with
  * stride(3)==1, stride(2)==D (kernels.cu:91); positions int64 [B,N,2] contiguous.
- * dtype: 0 = fp32, 1 = fp16, 2 = bf16.  fwd = +F0 forward, -F0 backward. */
+ * dtype: 0 = fp32, 1 = fp16, 2 = bf16, 3 = fp64 (the floating types the reference dispatches, kernels.cu:101, plus bf16;
+ * fp64 values are rotated in fp32 like the reference does through its float staging buffer, kernels.cu:30,66).
+ * fwd = +F0 forward, -F0 backward. */
 SPF_API int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
                int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd,
                void* stream);
+
+/* The two rope_2d calls of a self-attention block (croco/blocks.py:102-104: q = rope(q, xpos); k = rope(k, xpos))
+ * in ONE launch: q and k are same-shape, same-stride views (of the fused qkv tensor, blocks.py:97-98) sharing
+ * `positions`; cos/sin are evaluated once per (token, frequency) and applied to both. */
+SPF_API int spf_rope2d_qk(void* q, void* k, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
+                  int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd,
+                  void* stream);
 
 /* In-switch (NVLS multicast) sum all-reduce of one fp32 gradient bucket, in place.  Replaces the NCCL all-reduce torch DDP
  * issues for the replicated parameters' gradients (src/main.py:141-145).  multicast_bucket: the MULTICAST address of a
@@ -225,6 +234,13 @@ SPF_API int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_
  * cross-rank barriers on the same stream (every bucket final before; every slice broadcast after). */
 SPF_API int spf_multimem_allreduce_f32(float* multicast_bucket, int64_t numel, int32_t rank, int32_t world, int32_t n_blocks,
                                void* stream);
+
+/* The same reduction with both cross-rank barriers INSIDE the kernel (no separate barrier launches): signal_pads is a
+ * DEVICE array of `world` pointers, entry p = rank p's symmetric-memory signal pad (32-bit words, zero when idle) as mapped
+ * into this rank's address space; flags [pad_word_offset, pad_word_offset + 2 * n_blocks * world) of every pad are used,
+ * pad_words = words available per pad.  n_blocks must be the same on every rank. */
+SPF_API int spf_multimem_allreduce_f32_fused(float* multicast_bucket, int64_t numel, int32_t rank, int32_t world, int32_t n_blocks,
+                                     void* const* signal_pads, int32_t pad_word_offset, int32_t pad_words, void* stream);
 
 #ifdef __cplusplus
 }

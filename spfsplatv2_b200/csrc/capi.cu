@@ -246,16 +246,43 @@ int spf_multimem_allreduce_f32(float* multicast_bucket, int64_t numel, int32_t r
   return SPF_OK;
 }
 
-int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
-               int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
-  if (!tokens || !positions) return fail(SPF_ERR_BAD_ARG, "tokens / positions are NULL");
+int spf_multimem_allreduce_f32_fused(float* multicast_bucket, int64_t numel, int32_t rank, int32_t world, int32_t n_blocks,
+                                     void* const* signal_pads, int32_t pad_word_offset, int32_t pad_words, void* stream) {
+  if (!multicast_bucket || !signal_pads) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: NULL bucket / signal pads");
+  if (numel < 0 || (numel & 3) || (reinterpret_cast<uintptr_t>(multicast_bucket) & 15))
+    return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: bucket must be 16-byte aligned with numel % 4 == 0");
+  if (world < 1 || world > 1024 || rank < 0 || rank >= world) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: bad rank / world");
+  if (n_blocks < 1 || n_blocks > 148) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: n_blocks must be 1..148");
+  if (pad_word_offset < 0 || (int64_t)pad_word_offset + 2LL * n_blocks * world > pad_words)
+    return fail(SPF_ERR_WORKSPACE, "spf_multimem_allreduce_f32_fused: signal pad too small for 2 * n_blocks * world flags");
+  cudaError_t e = spf::launch_multimem_allreduce_f32_fused(multicast_bucket, numel, rank, world, n_blocks,
+                                                           reinterpret_cast<uint32_t* const*>(signal_pads), pad_word_offset,
+                                                           static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "multimem_allreduce_f32_fused");
+  return SPF_OK;
+}
+
+static int rope_common(void* q, void* k, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
+                       int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
+  if (!q || !positions) return fail(SPF_ERR_BAD_ARG, "tokens / positions are NULL");
   if (B < 0 || N < 0 || H < 0 || D < 0) return fail(SPF_ERR_BAD_ARG, "negative size");
   if (D % 4 != 0) return fail(SPF_ERR_BAD_ARG, "token dim must be multiple of 4");
-  if (dtype < 0 || dtype > 2) return fail(SPF_ERR_BAD_ARG, "dtype must be 0 (fp32), 1 (fp16) or 2 (bf16)");
-  cudaError_t e = spf::launch_rope2d(tokens, positions, B, N, H, D, stride_b, stride_n, dtype, base, fwd,
+  if (dtype < 0 || dtype > 3) return fail(SPF_ERR_BAD_ARG, "dtype must be 0 (fp32), 1 (fp16), 2 (bf16) or 3 (fp64)");
+  cudaError_t e = spf::launch_rope2d(q, k, positions, B, N, H, D, stride_b, stride_n, dtype, base, fwd,
                                      static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "rope2d");
   return SPF_OK;
+}
+
+int spf_rope2d(void* tokens, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
+               int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
+  return rope_common(tokens, nullptr, positions, B, N, H, D, stride_b, stride_n, dtype, base, fwd, stream);
+}
+
+int spf_rope2d_qk(void* q, void* k, const int64_t* positions, int32_t B, int32_t N, int32_t H, int32_t D,
+                  int64_t stride_b, int64_t stride_n, int32_t dtype, float base, float fwd, void* stream) {
+  if (!k) return fail(SPF_ERR_BAD_ARG, "k is NULL");
+  return rope_common(q, k, positions, B, N, H, D, stride_b, stride_n, dtype, base, fwd, stream);
 }
 
 }  // extern "C"

@@ -8,6 +8,12 @@
 // Layout: one thread per (token, half, VEC consecutive frequencies); it evaluates powf/sincosf once
 // and sweeps all H heads with 128-bit (fp32) / 64-bit (fp16, bf16) loads and stores -- no shared
 // memory, no per-head barrier, bf16 supported.  HBM-bound: 2 * B*N*H*D * sizeof(T) bytes.
+//
+// q and k of a self-attention block share their positions (blocks.py:97-104: both are views of one fused
+// qkv tensor): spf_rope2d_qk rotates BOTH in one launch, the thread reusing its cos/sin for the second
+// tensor -- half the launches and half the transcendental work of two rope_2d calls.
+// fp64 (dispatched by the reference, kernels.cu:101) follows the reference's arithmetic: the value is
+// rounded to fp32 (its shared-memory staging buffer is float, kernels.cu:30,66), rotated in fp32 and widened.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -29,12 +35,21 @@ template <> struct Cvt<__nv_bfloat16> {
   static __device__ __forceinline__ __nv_bfloat16 st(float v) { return __float2bfloat16_rn(v); }
 };
 
-template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+template <> struct Cvt<double> {
+  static __device__ __forceinline__ float ld(double v) { return (float)v; }
+  static __device__ __forceinline__ double st(float v) { return (double)v; }
+};
 
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC <= 16 ? sizeof(T) * VEC : 16) Pack { T v[VEC]; };
+
+// blockIdx.y selects a chunk of `hpt` heads: small problems (the decoder's 16 x 258 tokens) are split over the heads as
+// well so that enough loads are in flight to cover the HBM latency; the per-thread cos/sin work is repeated per chunk
+// (a few hundred instructions against kilobytes of traffic).  The two loads of a head (u, v) for BOTH tensors are issued
+// before anything is computed.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-rope2d_kernel(T* __restrict__ tokens, const int64_t* __restrict__ pos, int64_t n_tokens, int N, int H, int D,
-              int64_t sb, int64_t sn, float base, float fwd) {
+rope2d_kernel(T* __restrict__ tokens, T* __restrict__ tokens2, const int64_t* __restrict__ pos, int64_t n_tokens, int N,
+              int H, int D, int hpt, int64_t sb, int64_t sn, float base, float fwd) {
   const int Q = D >> 2;
   const int per_half = Q / VEC;
   const int per_token = 2 * per_half;
@@ -45,6 +60,16 @@ rope2d_kernel(T* __restrict__ tokens, const int64_t* __restrict__ pos, int64_t n
   const int X = r / per_half;            // 0: y half, 1: x half
   const int i0 = (r - X * per_half) * VEC;
   const int64_t b = tok / N, n = tok - b * N;
+  typedef Pack<T, VEC> PK;
+  const int h0 = blockIdx.y * hpt, h1 = min(H, h0 + hpt);
+  const int64_t off = b * sb + n * sn + (int64_t)h0 * D + X * 2 * Q + i0;
+  T* row = tokens + off;
+  T* row2 = tokens2 ? tokens2 + off : nullptr;
+  // the first head's loads go out BEFORE the position load and the powf / sincosf chain, so that the transcendental
+  // work (a few hundred cycles) overlaps the first trip to HBM instead of preceding it
+  PK u = *reinterpret_cast<const PK*>(row), v = *reinterpret_cast<const PK*>(row + Q);
+  PK u2 = u, v2 = v;
+  if (row2) { u2 = *reinterpret_cast<const PK*>(row2); v2 = *reinterpret_cast<const PK*>(row2 + Q); }
   const int p = (int)pos[tok * 2 + X];
   float cs[VEC], sn_[VEC];
 #pragma unroll
@@ -52,50 +77,69 @@ rope2d_kernel(T* __restrict__ tokens, const int64_t* __restrict__ pos, int64_t n
     const float ang = fwd * p / powf(base, (float)(i0 + k) / (float)Q);
     sincosf(ang, &sn_[k], &cs[k]);
   }
-  T* row = tokens + b * sb + n * sn + X * 2 * Q + i0;
-  typedef Pack<T, VEC> PK;
-  for (int h = 0; h < H; ++h, row += D) {
-    PK u = *reinterpret_cast<const PK*>(row);
-    PK v = *reinterpret_cast<const PK*>(row + Q);
+  auto rot = [&](const PK& a, const PK& c, T* dst) {
     PK uo, vo;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const float uf = Cvt<T>::ld(u.v[k]), vf = Cvt<T>::ld(v.v[k]);
+      const float uf = Cvt<T>::ld(a.v[k]), vf = Cvt<T>::ld(c.v[k]);
       uo.v[k] = Cvt<T>::st(uf * cs[k] - vf * sn_[k]);
       vo.v[k] = Cvt<T>::st(vf * cs[k] + uf * sn_[k]);
     }
-    *reinterpret_cast<PK*>(row) = uo;
-    *reinterpret_cast<PK*>(row + Q) = vo;
+    *reinterpret_cast<PK*>(dst) = uo;
+    *reinterpret_cast<PK*>(dst + Q) = vo;
+  };
+  for (int h = h0; h < h1; ++h) {
+    // next head's loads in flight while this head is rotated and stored
+    PK nu = u, nv = v, nu2 = u2, nv2 = v2;
+    if (h + 1 < h1) {
+      nu = *reinterpret_cast<const PK*>(row + D); nv = *reinterpret_cast<const PK*>(row + D + Q);
+      if (row2) { nu2 = *reinterpret_cast<const PK*>(row2 + D); nv2 = *reinterpret_cast<const PK*>(row2 + D + Q); }
+    }
+    rot(u, v, row);
+    if (row2) { rot(u2, v2, row2); row2 += D; }
+    row += D;
+    u = nu; v = nv; u2 = nu2; v2 = nv2;
   }
 }
 
 template <typename T>
-static cudaError_t launch_t(void* tokens, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
+static cudaError_t launch_t(void* tokens, void* tokens2, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
                             int64_t sn, float base, float fwd, cudaStream_t s) {
   const int Q = D / 4;
   const int64_t n_tokens = (int64_t)B * N;
-  const size_t vb = sizeof(T) * 4;
-  const bool vec4 = (Q % 4 == 0) && ((reinterpret_cast<uintptr_t>(tokens) % vb) == 0) &&
-                    ((sb * sizeof(T)) % vb == 0) && ((sn * sizeof(T)) % vb == 0);
+  constexpr int VW = sizeof(T) >= 4 ? 4 : 8;                  // elements per 128-bit access (fp64: two accesses)
+  const size_t vb = sizeof(T) * VW <= 16 ? sizeof(T) * VW : 16;
+  auto aligned = [&](int vec) {
+    const size_t bytes = sizeof(T) * vec <= 16 ? sizeof(T) * vec : 16;
+    return (Q % vec == 0) && ((reinterpret_cast<uintptr_t>(tokens) % bytes) == 0) &&
+           ((reinterpret_cast<uintptr_t>(tokens2) % bytes) == 0) && ((sb * sizeof(T)) % bytes == 0) &&
+           ((sn * sizeof(T)) % bytes == 0) && ((Q * sizeof(T)) % bytes == 0) && ((D * sizeof(T)) % bytes == 0);
+  };
+  (void)vb;
+  const int vec = aligned(VW) ? VW : (aligned(4) ? 4 : 1);
   if (n_tokens == 0 || H == 0) return cudaSuccess;
-  if (vec4) {
-    const int64_t threads = n_tokens * 2 * (Q / 4);
-    rope2d_kernel<T, 4><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>((T*)tokens, pos, n_tokens, N, H, D, sb,
-                                                                         sn, base, fwd);
-  } else {
-    const int64_t threads = n_tokens * 2 * Q;
-    rope2d_kernel<T, 1><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>((T*)tokens, pos, n_tokens, N, H, D, sb,
-                                                                         sn, base, fwd);
-  }
+  const int64_t threads = n_tokens * 2 * (Q / vec);
+  // heads per thread: all of them when the (token, frequency) threads alone fill the machine several times over,
+  // otherwise fewer, down to 1, until about 600 k threads (148 SMs x 2048 x 2) are in flight
+  int hpt = H;
+  while (hpt > 1 && threads * ((H + hpt - 1) / hpt) < 600000) hpt = (hpt + 1) / 2;
+  dim3 grid((unsigned)((threads + 255) / 256), (unsigned)((H + hpt - 1) / hpt));
+  if (vec == 8)
+    rope2d_kernel<T, (sizeof(T) >= 4 ? 4 : 8)><<<grid, 256, 0, s>>>((T*)tokens, (T*)tokens2, pos, n_tokens, N, H, D, hpt, sb, sn, base, fwd);
+  else if (vec == 4)
+    rope2d_kernel<T, 4><<<grid, 256, 0, s>>>((T*)tokens, (T*)tokens2, pos, n_tokens, N, H, D, hpt, sb, sn, base, fwd);
+  else
+    rope2d_kernel<T, 1><<<grid, 256, 0, s>>>((T*)tokens, (T*)tokens2, pos, n_tokens, N, H, D, hpt, sb, sn, base, fwd);
   return cudaGetLastError();
 }
 
-cudaError_t launch_rope2d(void* tokens, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
+cudaError_t launch_rope2d(void* tokens, void* tokens2, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
                           int64_t sn, int dtype, float base, float fwd, cudaStream_t s) {
   switch (dtype) {
-    case 0: return launch_t<float>(tokens, pos, B, N, H, D, sb, sn, base, fwd, s);
-    case 1: return launch_t<__half>(tokens, pos, B, N, H, D, sb, sn, base, fwd, s);
-    case 2: return launch_t<__nv_bfloat16>(tokens, pos, B, N, H, D, sb, sn, base, fwd, s);
+    case 0: return launch_t<float>(tokens, tokens2, pos, B, N, H, D, sb, sn, base, fwd, s);
+    case 1: return launch_t<__half>(tokens, tokens2, pos, B, N, H, D, sb, sn, base, fwd, s);
+    case 2: return launch_t<__nv_bfloat16>(tokens, tokens2, pos, B, N, H, D, sb, sn, base, fwd, s);
+    case 3: return launch_t<double>(tokens, tokens2, pos, B, N, H, D, sb, sn, base, fwd, s);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -108,11 +108,13 @@ cudaError_t launch_image_mse(const float* pred, const float* target, int n_image
                              float grad_scale, float* dL_dpred, float* partial, int blocks_per_image,
                              float* mse_per_image, float* mean_all, cudaStream_t s);
 cudaError_t launch_multimem_allreduce_f32(float* mc, int64_t numel, int rank, int world, int n_blocks, cudaStream_t s);
+cudaError_t launch_multimem_allreduce_f32_fused(float* mc, int64_t numel, int rank, int world, int n_blocks,
+                                                uint32_t* const* signal_pads, int pad_word_offset, cudaStream_t s);
 cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, float* scales, float* rots, float* sh,
                                    cudaStream_t s);
 cudaError_t launch_adapter_backward(const float* raw, const float* d_scales, const float* d_rots, const float* d_sh,
                                     int64_t n, int K, float eps, float* d_raw, cudaStream_t s);
-cudaError_t launch_rope2d(void* tokens, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
+cudaError_t launch_rope2d(void* tokens, void* tokens2, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
                           int64_t sn, int dtype, float base, float fwd, cudaStream_t s);
 
 }  // namespace spf

@@ -94,6 +94,9 @@ class GradAllReduce:
         self.nvls_blocks = int(os.environ.get("SPF_NVLS_BLOCKS", nvls_blocks or 16))
         self._symm: Dict[int, tuple] = {}      # data_ptr -> (tensor, symmetric-memory handle)
         self.nvls_error: Optional[str] = None  # why "auto" fell back to nccl, if it did
+        # cross-rank barriers inside the multimem kernel (signal pads) instead of two barrier launches around it;
+        # switched off (for every bucket, on every rank together) if the collective self-test fails with it
+        self.fused_barrier = os.environ.get("SPF_NVLS_FUSED_BARRIER", "1") != "0"
 
     # ---- symmetric-memory buckets (NVLS path) ----------------------------------------------------------------
     def alloc(self, numel: int, dtype: torch.dtype = torch.float32) -> Tensor:
@@ -118,15 +121,21 @@ class GradAllReduce:
             # that every rank has its bucket, then that every rank saw the right sums.
             if self._all_ranks(why is None):
                 self._symm[t.data_ptr()] = (t, hdl)
-                try:
-                    if not self._self_test(t, world):
-                        why = "multimem self-test gave wrong sums"
-                except Exception as exc:    # noqa: BLE001
-                    why = f"{type(exc).__name__}: {exc}"
-                if self._all_ranks(why is None):
-                    t.zero_()
-                    return t[:numel]
-            self._symm.clear()
+                for attempt in (0, 1):
+                    why = None
+                    try:
+                        if not self._self_test(t, world):
+                            why = "multimem self-test gave wrong sums"
+                    except Exception as exc:    # noqa: BLE001
+                        why = f"{type(exc).__name__}: {exc}"
+                    if self._all_ranks(why is None):
+                        t.zero_()
+                        return t[:numel]
+                    if not self.fused_barrier:
+                        break
+                    self.fused_barrier = False      # every rank takes this branch together: retry with barrier launches
+                    self.nvls_error = f"in-kernel barrier disabled ({why})"
+            self._symm.pop(t.data_ptr() if t is not None else 0, None)   # buckets handed out earlier stay on their backend
             why = why or "another rank failed"
             if self.backend == "nvls":
                 raise RuntimeError(f"nvls all-reduce unavailable: {why}")
@@ -165,12 +174,23 @@ class GradAllReduce:
         from . import _lib
         t, hdl = self._symm[g.data_ptr()]
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(self.stream):
-            hdl.barrier(channel=0)           # every rank's bucket is final
-            _lib.check(_lib.lib().spf_multimem_allreduce_f32(
-                ctypes.c_void_p(int(hdl.multicast_ptr) + int(self._mc_offset(hdl))), t.numel(), int(hdl.rank), int(hdl.world_size),
-                self.nvls_blocks, ctypes.c_void_p(self.stream.cuda_stream)), "spf_multimem_allreduce_f32")
-            hdl.barrier(channel=0)           # every slice has been broadcast to every rank
+        mc = ctypes.c_void_p(int(hdl.multicast_ptr) + int(self._mc_offset(hdl)))
+        pad_words = int(getattr(hdl, "signal_pad_size", 0)) // 4
+        # flags live in the upper half of the signal pad: torch's own barrier / signal ops use the low channels
+        base = pad_words // 2
+        fused = self.fused_barrier and pad_words - base >= 2 * self.nvls_blocks * int(hdl.world_size)
+        with torch.cuda.stream(self.stream), torch.cuda.device(self.device):
+            if fused:
+                _lib.check(_lib.lib().spf_multimem_allreduce_f32_fused(
+                    mc, t.numel(), int(hdl.rank), int(hdl.world_size), self.nvls_blocks,
+                    ctypes.c_void_p(int(hdl.signal_pad_ptrs_dev)), base, pad_words,
+                    ctypes.c_void_p(self.stream.cuda_stream)), "spf_multimem_allreduce_f32_fused")
+            else:
+                hdl.barrier(channel=0)           # every rank's bucket is final
+                _lib.check(_lib.lib().spf_multimem_allreduce_f32(
+                    mc, t.numel(), int(hdl.rank), int(hdl.world_size), self.nvls_blocks,
+                    ctypes.c_void_p(self.stream.cuda_stream)), "spf_multimem_allreduce_f32")
+                hdl.barrier(channel=0)           # every slice has been broadcast to every rank
 
     def _ensure_bucket(self, numel: int, dtype: torch.dtype):
         if self._bucket is None or self._bucket.numel() < numel or self._bucket.dtype != dtype:
@@ -222,6 +242,56 @@ class GradAllReduce:
     def wait(self) -> None:
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
+class NvlsCommHook:
+    """DDP communication hook: ``ddp.register_comm_hook(None, NvlsCommHook(reducer))`` replaces the NCCL all-reduce that
+    torch DDP issues per gradient bucket (the reference trains with Lightning's "ddp_find_unused_parameters_true"
+    strategy, /root/reference/src/main.py:141-145) by this repo's reducer: the bucket is copied into a symmetric-memory
+    twin (allocated collectively the first time a bucket of that index and size is seen -- DDP presents buckets in the
+    same order on every rank), summed inside the NVSwitch by the multimem kernel on the reducer's side stream, averaged
+    over the world size (DDP's contract for the default hook) and copied back.  Falls back to torch.distributed when
+    the reducer has no NVLS (CPU / gloo, single node without multicast): same plumbing, same result."""
+
+    def __init__(self, reducer: "GradAllReduce"):
+        self.reducer = reducer
+        self._twins: Dict[tuple, Tensor] = {}
+
+    def __call__(self, state, bucket) -> "torch.futures.Future[Tensor]":
+        buf = bucket.buffer()
+        red = self.reducer
+        world = dist.get_world_size(red.group)
+        fut: torch.futures.Future = torch.futures.Future(devices=[red.device]) if red.device.type == "cuda" else torch.futures.Future()
+        key = (bucket.index(), buf.numel(), buf.dtype)
+        twin = self._twins.get(key)
+        if twin is None:
+            twin = red.alloc(buf.numel(), buf.dtype)      # collective
+            self._twins[key] = twin
+        if red.stream is not None:
+            red.stream.wait_stream(torch.cuda.current_stream(red.device))
+            with torch.cuda.stream(red.stream):
+                twin.copy_(buf)
+                red.launch([twin])                        # enqueues on red.stream (already current: wait_stream is a no-op)
+                torch.mul(twin, 1.0 / world, out=buf)
+                fut.set_result(buf)                       # records the side stream: consumers wait on it, not on the host
+        else:
+            twin.copy_(buf)
+            red.launch([twin])
+            torch.mul(twin, 1.0 / world, out=buf)
+            fut.set_result(buf)
+        return fut
+
+
+def nvls_comm_hook(reducer: "GradAllReduce"):
+    """``ddp.register_comm_hook(None, nvls_comm_hook(reducer))``: a plain function (torch DDP inspects the hook's
+    ``__name__`` and its annotations as objects) around an NvlsCommHook."""
+    impl = NvlsCommHook(reducer)
+
+    def nvls_allreduce_hook(state, bucket):
+        return impl(state, bucket)
+    nvls_allreduce_hook.__annotations__ = {"bucket": dist.GradBucket, "return": torch.futures.Future[torch.Tensor]}
+    nvls_allreduce_hook.impl = impl
+    return nvls_allreduce_hook
 
 
 def render_views_sharded(render_view: Callable[[int], Tensor], loss_of_view: Callable[[int, Tensor], Tensor],

@@ -48,6 +48,12 @@ def make_rope():
     spec.loader.exec_module(mod)
     assert mod.RoPE2D.__name__ == "RoPE2D" and hasattr(mod.RoPE2D, "apply_rope1d"), "expected the torch fallback"
 
+    # VGGT's own pure-torch RoPE (vggt/layers/rope.py:62-188), loaded from where it lies
+    vspec = importlib.util.spec_from_file_location(
+        "ref_vggt_rope", os.path.join(REF, "src/model/encoder/backbone/vggt/layers/rope.py"))
+    vmod = importlib.util.module_from_spec(vspec)
+    vspec.loader.exec_module(vmod)
+
     out = {}
     cases = {   # name: (B, N, H, D, max_pos, base)
         "small": (2, 7, 3, 16, 5, 100.0),
@@ -73,6 +79,11 @@ def make_rope():
         out[f"{name}_fwd"] = fwd.numpy()
         out[f"{name}_bwd"] = bwd.numpy()
         out[f"{name}_pytorch_fwd"] = py.numpy()
+        if D % 2 == 0:
+            # VGGT layout: tokens [B, H, N, D]; its positions come from PositionGetter (0-based grid coordinates)
+            vg = vmod.RotaryPositionEmbedding2D(frequency=base)(tok.transpose(1, 2).contiguous(), pos)
+            out[f"{name}_vggt_fwd"] = vg.transpose(1, 2).contiguous().numpy()
+            print(f"rope {name}: vggt-vs-cpp max|d| = {(out[f'{name}_vggt_fwd'] - fwd.numpy()).__abs__().max():.2e}")
         print(f"rope {name}: cpp-vs-pytorch max|d| = {(fwd - py).abs().max():.2e}, round trip {(rt - tok).abs().max():.2e}")
     np.savez_compressed(os.path.join(HERE, "rope_ref.npz"), **out)
 

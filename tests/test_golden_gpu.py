@@ -86,6 +86,50 @@ def test_rope_module_strided_view_autograd_and_errors(rope_gold):
     rope_2d(empty, torch.zeros(0, 4, 2, dtype=torch.int64, device=D0), 100.0, 1.0)   # empty batch is a no-op
 
 
+def test_rope_qk_single_launch_and_fp64(rope_gold):
+    """q and k of the fused qkv tensor rotated by ONE launch (spf_rope2d_qk; blocks.py:97-104) are bit-identical to two
+    rope_2d calls, forward and backward; v stays untouched.  fp64 (dispatched by the reference, kernels.cu:101) follows
+    the reference's arithmetic: rounded to fp32, rotated, widened -- checked against the fp32 fixture path."""
+    from spfsplatv2_b200.curope import cuRoPE2D, rope_2d, rope_2d_qk
+    torch.manual_seed(1)
+    B, N, H, D = 2, 23, 12, 64
+    x = torch.randn(B, N, 3 * H * D, device=D0)
+    pos = torch.randint(0, 16, (B, N, 2), device=D0)
+    wq, wk = torch.randn(B, H, N, D, device=D0), torch.randn(B, H, N, D, device=D0)
+    rope = cuRoPE2D(100.0, 1.0)
+
+    def run(xx, fused):
+        qkv = (xx * 1.0).reshape(B, N, 3, H, D)
+        if fused:
+            qkv = rope.forward_qkv(qkv, pos)
+        qkv = qkv.transpose(1, 3)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        if not fused:
+            q = rope(q, pos)
+            k = rope(k, pos)
+        return q, k, v
+    outs = []
+    for fused in (False, True):
+        xg = x.clone().requires_grad_()
+        q, k, v = run(xg, fused)
+        ((q * wq).sum() + (k * wk).sum() + v.sum()).backward()
+        outs.append((q.detach().clone(), k.detach().clone(), v.detach().clone(), xg.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[1][2], x.reshape(B, N, 3, H, D).transpose(1, 3)[:, :, 2])      # v untouched
+    with pytest.raises(RuntimeError, match="same shape"):
+        rope_2d_qk(torch.zeros(1, 4, 2, 8, device=D0), torch.zeros(1, 4, 2, 16, device=D0),
+                   torch.zeros(1, 4, 2, dtype=torch.int64, device=D0), 100.0, 1.0)
+    # fp64
+    tok, p, base = rope_gold["vit_tokens"], rope_gold["vit_pos"], float(rope_gold["vit_base"])
+    t64 = torch.from_numpy(tok).to(D0, torch.float64) * (1.0 + 2.0 ** -30)       # not representable in fp32
+    t32 = t64.float()
+    rope_2d(t64, torch.from_numpy(p).to(D0), base, 1.0)
+    rope_2d(t32, torch.from_numpy(p).to(D0), base, 1.0)
+    assert t64.dtype == torch.float64 and torch.equal(t64, t32.double())
+    assert (t32.cpu() - torch.from_numpy(rope_gold["vit_fwd"])).abs().max().item() < 2e-5
+
+
 def test_cuda_decoder_matches_reference_decoder_golden():
     """Our DecoderSplattingCUDA (CUDA path, batched, fused camera setup) vs the reference's unmodified decoder on the
     same inputs: color / depth / loss and all gradients incl. camera pose."""
@@ -175,8 +219,9 @@ def test_fused_image_losses_match_reference_definitions():
 
 
 def test_vggt_rope_module_matches_reference_pytorch_rope(rope_gold):
-    """RotaryPositionEmbedding2D (VGGT backbone, vggt/layers/rope.py:62-188 -- the same function as the CroCo RoPE2D whose
-    outputs are in the golden file): out of place, [B,H,N,D] layout, differentiable."""
+    """RotaryPositionEmbedding2D (VGGT backbone) against the outputs of VGGT's OWN module (vggt/layers/rope.py:62-188,
+    run by tests/golden/make_golden.py from where it lies under /root/reference): out of place, [B,H,N,D] layout,
+    differentiable."""
     from spfsplatv2_b200.curope import RotaryPositionEmbedding2D
     tok = torch.from_numpy(rope_gold["vit_tokens"]).to(D0)           # [B,N,H,D]
     pos = torch.from_numpy(rope_gold["vit_pos"]).to(D0)
@@ -185,8 +230,9 @@ def test_vggt_rope_module_matches_reference_pytorch_rope(rope_gold):
     y = rope(x, pos)
     assert y.shape == x.shape and y.data_ptr() != x.data_ptr()
     assert torch.equal(x.detach(), tok.transpose(1, 2))              # input untouched
-    want = torch.from_numpy(rope_gold["vit_pytorch_fwd"]).to(D0).transpose(1, 2)
+    want = torch.from_numpy(rope_gold["vit_vggt_fwd"]).to(D0).transpose(1, 2)
     assert (y - want).abs().max().item() < 2e-5
+    assert (y - torch.from_numpy(rope_gold["vit_pytorch_fwd"]).to(D0).transpose(1, 2)).abs().max().item() < 2e-5
     w = torch.randn_like(y)
     (y * w).sum().backward()
     gwant = RO.rope_2d(w.transpose(1, 2).contiguous().cpu().numpy(), rope_gold["vit_pos"], float(rope_gold["vit_base"]), -1.0)
