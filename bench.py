@@ -118,8 +118,30 @@ def _make_inputs(workload: str, rank: int, pin: bool):
                 opacities=sc.opacities, extrinsics=sc.extrinsics, intrinsics=sc.intrinsics, near=sc.near, far=sc.far)
     host["gt"] = torch.rand(b, 1, 3, h, w, generator=torch.Generator().manual_seed(rank))
     if pin:
-        host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+        host = {k: _pin(v.contiguous()) for k, v in host.items()}
     return sc, host
+
+
+_wc_keepalive = []
+
+
+def _pin(t):
+    """Page-locked copy of a host tensor.  SPF_PIN=wc allocates it write-combined (cudaHostAllocWriteCombined: the GPU's
+    PCIe reads do not snoop the CPU caches) -- an A/B switch for the end-to-end loop; default: torch's pin_memory()."""
+    if os.environ.get("SPF_PIN", "") != "wc":
+        return t.pin_memory()
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    ptr = ctypes.c_void_p()
+    nbytes = t.numel() * t.element_size()
+    rc = rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(max(nbytes, 1)), ctypes.c_uint(0x04 | 0x01))
+    if rc != 0:
+        return t.pin_memory()
+    buf = (ctypes.c_byte * nbytes).from_address(ptr.value)
+    out = torch.frombuffer(buf, dtype=t.dtype, count=t.numel()).view(t.shape)
+    out.copy_(t)
+    _wc_keepalive.append((buf, ptr))
+    return out
 
 
 def _step(dec, G, dev_in, leaves_keys=("means", "rotations", "scales", "harmonics", "opacities")):
@@ -178,11 +200,11 @@ def run_ours(args):
             ev.record(torch.cuda.current_stream(dev))
 
     def ar_begin():
-        """Dependency a training loop imposes: step k may start once the gradient all-reduce of step k-1 has finished
-        (its sums feed the optimizer step k's forward reads; one step of slack = the usual pipelined / delayed-update
-        form).  dep == "none" drops it (the reduction is then never on the critical path)."""
+        """Dependency a pipelined training loop imposes: step k+1 may start once the gradient all-reduce of step k-1 has
+        finished (the reduction of step k-1 overlaps step k and feeds the parameter update step k+1 reads; it is also
+        when bucket (k+1) % 2 is free again).  dep == "none" drops it (the reduction is then never on the critical path)."""
         if world > 1 and ar_state["dep"] == "lag1":
-            torch.cuda.current_stream(dev).wait_event(ar_done[(ar_state["k"] + 1) % 2])
+            torch.cuda.current_stream(dev).wait_event(ar_done[ar_state["k"] % 2])
 
     def ar_launch():
         """The step's replicated-parameter gradient: every rank writes rank+1 into the bucket (stand-in for the
@@ -318,6 +340,15 @@ def run_ours(args):
     ms_e2e, wall_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     if world > 1:
         ar_check()
+
+    # The same host->device copies ALONE (no kernels), all ranks at once: the ceiling the host side (PCIe root ports,
+    # host memory, the hypervisor) puts under the end-to-end number at this rank count.
+    def copy_only():
+        with torch.cuda.stream(copy_stream):
+            for name, v in host.items():
+                e2e_bufs[0][name].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+    ms_copy, _ = timed(copy_only, args.steps, 3)
     clocks = sampler.stop() if rank == 0 else None
 
     views_total = b * world
@@ -363,7 +394,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {desc}", "views_per_step_per_gpu": b, "gaussians_per_scene": P,
                        "duplicates_per_step": N, "image": [h, w], "sh_degree": 4,
                        "parallelism": (f"dp{world} (scenes sharded over ranks; one 64 MiB gradient-bucket sum all-reduce per step on a side stream, "
-                                       f"{ar_backend}{' + in-kernel barriers' if ar_backend == 'nvls' and reducer.fused_barrier else ''}; step k waits for the "
+                                       f"{ar_backend}{' + in-kernel barriers' if ar_backend == 'nvls' and reducer.fused_barrier else ''}; step k+1 waits for the "
                                        f"reduction of step k-1; sums verified after the timed loop)") if world > 1 else "single GPU",
                        "value_without_allreduce_dependency": round(views_total * args.steps / (ms_nodep / 1e3), 2) if ms_nodep else None,
                        "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step > 126 MB L2, no explicit flush",
@@ -371,7 +402,12 @@ def run_ours(args):
                        "loss": "fused MSE (spfsplatv2_b200.loss.mse_loss)",
                        "numa_node_rank0": numa_node},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": round(max(ms_e2e, wall_e2e) / args.steps, 4)},
+                    "ms_per_step": round(max(ms_e2e, wall_e2e) / args.steps, 4),
+                    # copy-only loop, slowest rank: what the host lets ONE rank pull while all `world` ranks pull together
+                    "h2d_copy_only_ms_per_step": round(ms_copy / args.steps, 4),
+                    "h2d_copy_only_gbs_per_rank": round(h2d_bytes / (ms_copy / args.steps * 1e-3) / 1e9, 2),
+                    "h2d_copy_only_gbs_all_ranks": round(world * h2d_bytes / (ms_copy / args.steps * 1e-3) / 1e9, 2),
+                    "copy_bound_views_per_s": round(views_total / (ms_copy / args.steps * 1e-3), 2)},
             "gpu_launches": (13 + (1 if ar_backend == "nvls" else 0)) * args.steps,   # (+ the multimem all-reduce kernel at N>1) camera fwd/bwd, project fwd/bwd, scan, emit, sort+pack, blend fwd, blend bwd (log + fallback), pose reduce, fused MSE loss (2)
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],

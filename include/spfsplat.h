@@ -211,6 +211,17 @@ SPF_API int spf_adapter_forward(const float* raw, int64_t n, int32_t sh_coeffs, 
 SPF_API int spf_adapter_backward(const float* raw, const float* dL_dscales, const float* dL_drotations,
                          const float* dL_dharmonics, int64_t n, int32_t sh_coeffs, float eps, float* dL_draw, void* stream);
 
+/* The encoder head's whole post-processing in one pass: rows [n, 1 + 7 + 3*sh_coeffs] = the 83-channel Gaussian-head output
+ * (density logit first, /root/reference/src/model/encoder/encoder_spfsplatv2.py:255-268) -> opacities [n] by
+ * EncoderSPFSplatV2.map_pdf_to_opacity (:146-159: p = sigmoid(logit), 0.5 * (1 - (1-p)^e + p^(1/e)); `exponent` e = 2^x with
+ * x from the caller's warm-up schedule, 1 for the shipped config spfsplatv2.yaml:6-9) plus the adapter's scales / rotations /
+ * harmonics as above.  Backward: any upstream gradient may be NULL (= zero). */
+SPF_API int spf_head_forward(const float* raw, int64_t n, int32_t sh_coeffs, float eps, float exponent, float* opacities,
+                     float* scales, float* rotations, float* harmonics, void* stream);
+SPF_API int spf_head_backward(const float* raw, const float* dL_dopacities, const float* dL_dscales, const float* dL_drotations,
+                      const float* dL_dharmonics, int64_t n, int32_t sh_coeffs, float eps, float exponent, float* dL_draw,
+                      void* stream);
+
 /* 2-D RoPE, in place.  Replaces rope_2d (curope.cpp:49-65).  tokens: [B,N,H,D] view with
  * stride(3)==1, stride(2)==D (kernels.cu:91); positions int64 [B,N,2] contiguous.
  * dtype: 0 = fp32, 1 = fp16, 2 = bf16, 3 = fp64 (the floating types the reference dispatches, kernels.cu:101, plus bf16;

@@ -53,6 +53,56 @@ class _Adapter(torch.autograd.Function):
         return d_raw.view(shape), None, None
 
 
+class _Head(torch.autograd.Function):
+    """83-channel head output -> (opacities, scales, rotations, harmonics) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, raw: Tensor, d_sh: int, eps: float, exponent: float):
+        if not raw.is_cuda:
+            raise RuntimeError("spfsplatv2_b200.adapter needs CUDA tensors (no CPU fallback on the product path)")
+        lead = raw.shape[:-1]
+        r = raw.detach().float().contiguous().view(-1, raw.shape[-1])
+        n, dev = r.shape[0], r.device
+        opac = torch.empty(n, dtype=torch.float32, device=dev)
+        scales = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        rots = torch.empty(n, 4, dtype=torch.float32, device=dev)
+        sh = torch.empty(n, 3, d_sh, dtype=torch.float32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            L.check(L.lib().spf_head_forward(_p(r), n, d_sh, float(eps), float(exponent), _p(opac), _p(scales), _p(rots), _p(sh),
+                                             stream), "spf_head_forward")
+        ctx.save_for_backward(r)
+        ctx.meta = (d_sh, eps, exponent, raw.shape)
+        return opac.view(*lead), scales.view(*lead, 3), rots.view(*lead, 4), sh.view(*lead, 3, d_sh)
+
+    @staticmethod
+    def backward(ctx, g_opac, g_scales, g_rots, g_sh):
+        (r,) = ctx.saved_tensors
+        d_sh, eps, exponent, shape = ctx.meta
+        c = lambda g: None if g is None else g.float().contiguous()
+        go, gs, gr, gh = c(g_opac), c(g_scales), c(g_rots), c(g_sh)
+        d_raw = torch.empty_like(r)
+        stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+        with torch.cuda.device(r.device):
+            L.check(L.lib().spf_head_backward(_p(r), _p(go), _p(gs), _p(gr), _p(gh), r.shape[0], d_sh, float(eps), float(exponent),
+                                              _p(d_raw), stream), "spf_head_backward")
+        return d_raw.view(shape), None, None, None
+
+
+@dataclass
+class OpacityMappingCfg:
+    """encoder.opacity_mapping of the reference (config/model/encoder/spfsplatv2.yaml:6-9)."""
+    initial: float = 0.0
+    final: float = 0.0
+    warm_up: int = 1
+
+
+def opacity_exponent(cfg: OpacityMappingCfg, global_step: int) -> float:
+    """The exponent schedule of EncoderSPFSplatV2.map_pdf_to_opacity (encoder_spfsplatv2.py:153-155)."""
+    x = cfg.initial + min(global_step / cfg.warm_up, 1) * (cfg.final - cfg.initial)
+    return 2 ** x
+
+
 @dataclass
 class GaussianAdapterCfg:
     gaussian_scale_min: float
@@ -83,3 +133,16 @@ class UnifiedGaussianAdapter(torch.nn.Module):
         cov = torch.zeros((), dtype=means.dtype, device=means.device).expand(*lead, 3, 3)
         return Gaussians(means=means, covariances=cov, rotations=rotations.expand(*lead, 4), scales=scales.expand(*lead, 3),
                          harmonics=sh.expand(*lead, 3, self.d_sh), opacities=opacities)
+
+    def forward_head(self, means: Tensor, head_out: Tensor, opacity_mapping: OpacityMappingCfg = OpacityMappingCfg(),
+                     global_step: int = 0, eps: float = 1e-8) -> Gaussians:
+        """The encoder's whole Gaussian post-processing (encoder_spfsplatv2.py:255-268) fused: ``head_out`` [..., 1 + d_in]
+        is the Gaussian head's output with the density logit in channel 0; replaces
+        ``densities = head_out[..., 0].sigmoid(); opacities = map_pdf_to_opacity(densities, global_step)`` followed by
+        ``gaussian_adapter.forward(means, opacities, head_out[..., 1:])`` -- one kernel instead of ~15, no intermediate
+        opacity / density tensors, the raw rows read once."""
+        if head_out.shape[-1] != self.d_in + 1:
+            raise ValueError(f"head output has {head_out.shape[-1]} channels, expected {self.d_in + 1}")
+        opac, scales, rotations, sh = _Head.apply(head_out, self.d_sh, eps, opacity_exponent(opacity_mapping, global_step))
+        cov = torch.zeros((), dtype=means.dtype, device=means.device).expand(*opac.shape, 3, 3)
+        return Gaussians(means=means, covariances=cov, rotations=rotations, scales=scales, harmonics=sh, opacities=opac)

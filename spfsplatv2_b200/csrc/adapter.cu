@@ -5,6 +5,9 @@
 //     scales    = clamp_max(0.001 * softplus(raw[0:3]), 0.3)
 //     rotations = raw[3:7] / (|raw[3:7]| + eps)
 //     harmonics = raw[7:].view(3, K) * sh_mask          (sh_mask[0] = 1, degree d >= 1: 0.1 * 0.25^d, :42-48)
+// and, when the row carries the density logit in front (the encoder head's 83-channel output,
+// encoder_spfsplatv2.py:255-268), the opacity mapping of EncoderSPFSplatV2.map_pdf_to_opacity (:146-159):
+//     p = sigmoid(raw[0]);  opacity = 0.5 * (1 - (1 - p)^e + p^(1/e)),  e = 2^x  (x from the warm-up schedule, host side)
 // HBM-bound: 2 * (7 + 3K) * 4 bytes per Gaussian each way.  A block stages 128 raw rows in shared memory with coalesced
 // 128-bit loads and writes the three outputs element-parallel (coalesced) -- no per-thread 328-byte strides.
 #include "spf_device.cuh"
@@ -22,15 +25,24 @@ __device__ __forceinline__ float sh_mask_of(int k) {
   return m[deg];
 }
 
+// `dens` = 1: rows are [density logit, 7 + 3K parameters] and `opac` receives the mapped opacity; 0: rows are the 7 + 3K
+// parameters only (the adapter's own contract).
 __global__ void __launch_bounds__(AD_THREADS)
-adapter_forward_kernel(const float* __restrict__ raw, int64_t n, int K, float eps, float* __restrict__ scales,
-                       float* __restrict__ rots, float* __restrict__ sh) {
-  extern __shared__ __align__(16) float tile[];
-  const int R = 7 + 3 * K;
+adapter_forward_kernel(const float* __restrict__ raw_all, int64_t n, int K, float eps, int dens, float exponent,
+                       float* __restrict__ scales, float* __restrict__ rots, float* __restrict__ sh, float* __restrict__ opac) {
+  extern __shared__ __align__(16) float tile_all[];
+  const int R = dens + 7 + 3 * K;
   const int64_t g0 = (int64_t)blockIdx.x * AD_ROWS;
   const int rows = (int)min((int64_t)AD_ROWS, n - g0);
-  block_copy_g2s(tile, raw + g0 * R, rows * R, R, R, threadIdx.x, AD_THREADS);
+  block_copy_g2s(tile_all, raw_all + g0 * R, rows * R, R, R, threadIdx.x, AD_THREADS);
   __syncthreads();
+  const float* tile = tile_all + dens;           // row g of the 7 + 3K parameters starts at tile + g * R
+  if (dens && opac) {
+    for (int g = threadIdx.x; g < rows; g += AD_THREADS) {
+      const float p = 1.0f / (1.0f + expf(-tile_all[g * R]));
+      opac[g0 + g] = 0.5f * ((1.0f - powf(1.0f - p, exponent)) + powf(p, 1.0f / exponent));
+    }
+  }
   for (int i = threadIdx.x; i < rows * 3; i += AD_THREADS) {
     const int g = i / 3, c = i - g * 3;
     scales[g0 * 3 + i] = fminf(0.001f * softplus_t(tile[g * R + c]), 0.3f);
@@ -50,15 +62,26 @@ adapter_forward_kernel(const float* __restrict__ raw, int64_t n, int K, float ep
 
 __global__ void __launch_bounds__(AD_THREADS)
 adapter_backward_kernel(const float* __restrict__ raw, const float* __restrict__ d_scales, const float* __restrict__ d_rots,
-                        const float* __restrict__ d_sh, int64_t n, int K, float eps, float* __restrict__ d_raw) {
-  extern __shared__ __align__(16) float tile[];      // raw rows, overwritten in place by d_raw rows
+                        const float* __restrict__ d_sh, const float* __restrict__ d_opac, int64_t n, int K, float eps, int dens,
+                        float exponent, float* __restrict__ d_raw) {
+  extern __shared__ __align__(16) float tile_all[];      // raw rows, overwritten in place by d_raw rows
   __shared__ float dq[AD_ROWS * 4];
-  const int R = 7 + 3 * K;
+  const int R = dens + 7 + 3 * K;
   const int64_t g0 = (int64_t)blockIdx.x * AD_ROWS;
   const int rows = (int)min((int64_t)AD_ROWS, n - g0);
-  block_copy_g2s(tile, raw + g0 * R, rows * R, R, R, threadIdx.x, AD_THREADS);
+  block_copy_g2s(tile_all, raw + g0 * R, rows * R, R, R, threadIdx.x, AD_THREADS);
   for (int i = threadIdx.x; i < rows * 4; i += AD_THREADS) dq[i] = d_rots ? d_rots[g0 * 4 + i] : 0.0f;
   __syncthreads();
+  float* tile = tile_all + dens;
+  if (dens) {
+    // d opacity / d logit = 0.5 (e (1-p)^(e-1) + (1/e) p^(1/e-1)) p (1-p)
+    for (int g = threadIdx.x; g < rows; g += AD_THREADS) {
+      const float p = 1.0f / (1.0f + expf(-tile_all[g * R]));
+      const float ie = 1.0f / exponent;
+      const float dy = 0.5f * (exponent * powf(1.0f - p, exponent - 1.0f) + ie * powf(p, ie - 1.0f));
+      tile_all[g * R] = d_opac ? d_opac[g0 + g] * dy * (p * (1.0f - p)) : 0.0f;
+    }
+  }
   // quaternion part first (needs all four raw components of a row before any is overwritten): one thread per row
   for (int g = threadIdx.x; g < rows; g += AD_THREADS) {
     float* q = tile + g * R + 3;
@@ -85,31 +108,33 @@ adapter_backward_kernel(const float* __restrict__ raw, const float* __restrict__
     tile[g * R + 7 + j] = d_sh ? d_sh[g0 * W + i] * sh_mask_of(j % K) : 0.0f;
   }
   __syncthreads();
-  block_copy_s2g(d_raw + g0 * R, tile, rows * R, R, R, threadIdx.x, AD_THREADS);
+  block_copy_s2g(d_raw + g0 * R, tile_all, rows * R, R, R, threadIdx.x, AD_THREADS);
 }
 
-cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, float* scales, float* rots, float* sh,
-                                   cudaStream_t s) {
+cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, int dens, float exponent, float* scales,
+                                   float* rots, float* sh, float* opac, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  const size_t smem = (size_t)AD_ROWS * (7 + 3 * K) * sizeof(float);
+  const size_t smem = (size_t)AD_ROWS * (dens + 7 + 3 * K) * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(adapter_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  adapter_forward_kernel<<<(unsigned)((n + AD_ROWS - 1) / AD_ROWS), AD_THREADS, smem, s>>>(raw, n, K, eps, scales, rots, sh);
+  adapter_forward_kernel<<<(unsigned)((n + AD_ROWS - 1) / AD_ROWS), AD_THREADS, smem, s>>>(raw, n, K, eps, dens, exponent, scales,
+                                                                                         rots, sh, opac);
   return cudaGetLastError();
 }
 
 cudaError_t launch_adapter_backward(const float* raw, const float* d_scales, const float* d_rots, const float* d_sh,
-                                    int64_t n, int K, float eps, float* d_raw, cudaStream_t s) {
+                                    const float* d_opac, int64_t n, int K, float eps, int dens, float exponent, float* d_raw,
+                                    cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  const size_t smem = (size_t)AD_ROWS * (7 + 3 * K) * sizeof(float);
+  const size_t smem = (size_t)AD_ROWS * (dens + 7 + 3 * K) * sizeof(float);
   if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(adapter_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  adapter_backward_kernel<<<(unsigned)((n + AD_ROWS - 1) / AD_ROWS), AD_THREADS, smem, s>>>(raw, d_scales, d_rots, d_sh, n, K,
-                                                                                          eps, d_raw);
+  adapter_backward_kernel<<<(unsigned)((n + AD_ROWS - 1) / AD_ROWS), AD_THREADS, smem, s>>>(raw, d_scales, d_rots, d_sh, d_opac,
+                                                                                          n, K, eps, dens, exponent, d_raw);
   return cudaGetLastError();
 }
 

@@ -217,7 +217,7 @@ int spf_adapter_forward(const float* raw, int64_t n, int32_t sh_coeffs, float ep
                         float* harmonics, void* stream) {
   if (!raw || !scales || !rotations || !harmonics) return fail(SPF_ERR_BAD_ARG, "spf_adapter_forward: NULL pointer");
   if (n < 0 || sh_coeffs < 1 || sh_coeffs > spf::MAX_SH_COEFFS) return fail(SPF_ERR_BAD_ARG, "spf_adapter_forward: bad sizes");
-  cudaError_t e = spf::launch_adapter_forward(raw, n, sh_coeffs, eps, scales, rotations, harmonics,
+  cudaError_t e = spf::launch_adapter_forward(raw, n, sh_coeffs, eps, 0, 1.0f, scales, rotations, harmonics, nullptr,
                                               static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "adapter_forward");
   return SPF_OK;
@@ -227,9 +227,32 @@ int spf_adapter_backward(const float* raw, const float* dL_dscales, const float*
                          int64_t n, int32_t sh_coeffs, float eps, float* dL_draw, void* stream) {
   if (!raw || !dL_draw) return fail(SPF_ERR_BAD_ARG, "spf_adapter_backward: NULL pointer");
   if (n < 0 || sh_coeffs < 1 || sh_coeffs > spf::MAX_SH_COEFFS) return fail(SPF_ERR_BAD_ARG, "spf_adapter_backward: bad sizes");
-  cudaError_t e = spf::launch_adapter_backward(raw, dL_dscales, dL_drotations, dL_dharmonics, n, sh_coeffs, eps, dL_draw,
-                                               static_cast<cudaStream_t>(stream));
+  cudaError_t e = spf::launch_adapter_backward(raw, dL_dscales, dL_drotations, dL_dharmonics, nullptr, n, sh_coeffs, eps, 0, 1.0f,
+                                               dL_draw, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "adapter_backward");
+  return SPF_OK;
+}
+
+int spf_head_forward(const float* raw, int64_t n, int32_t sh_coeffs, float eps, float exponent, float* opacities, float* scales,
+                     float* rotations, float* harmonics, void* stream) {
+  if (!raw || !opacities || !scales || !rotations || !harmonics) return fail(SPF_ERR_BAD_ARG, "spf_head_forward: NULL pointer");
+  if (n < 0 || sh_coeffs < 1 || sh_coeffs > spf::MAX_SH_COEFFS) return fail(SPF_ERR_BAD_ARG, "spf_head_forward: bad sizes");
+  if (!(exponent > 0.0f)) return fail(SPF_ERR_BAD_ARG, "spf_head_forward: exponent must be positive");
+  cudaError_t e = spf::launch_adapter_forward(raw, n, sh_coeffs, eps, 1, exponent, scales, rotations, harmonics, opacities,
+                                              static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "head_forward");
+  return SPF_OK;
+}
+
+int spf_head_backward(const float* raw, const float* dL_dopacities, const float* dL_dscales, const float* dL_drotations,
+                      const float* dL_dharmonics, int64_t n, int32_t sh_coeffs, float eps, float exponent, float* dL_draw,
+                      void* stream) {
+  if (!raw || !dL_draw) return fail(SPF_ERR_BAD_ARG, "spf_head_backward: NULL pointer");
+  if (n < 0 || sh_coeffs < 1 || sh_coeffs > spf::MAX_SH_COEFFS) return fail(SPF_ERR_BAD_ARG, "spf_head_backward: bad sizes");
+  if (!(exponent > 0.0f)) return fail(SPF_ERR_BAD_ARG, "spf_head_backward: exponent must be positive");
+  cudaError_t e = spf::launch_adapter_backward(raw, dL_dscales, dL_drotations, dL_dharmonics, dL_dopacities, n, sh_coeffs, eps, 1,
+                                               exponent, dL_draw, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "head_backward");
   return SPF_OK;
 }
 

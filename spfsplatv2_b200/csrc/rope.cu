@@ -44,8 +44,10 @@ template <typename T, int VEC> struct alignas(sizeof(T) * VEC <= 16 ? sizeof(T) 
 
 // blockIdx.y selects a chunk of `hpt` heads: small problems (the decoder's 16 x 258 tokens) are split over the heads as
 // well so that enough loads are in flight to cover the HBM latency; the per-thread cos/sin work is repeated per chunk
-// (a few hundred instructions against kilobytes of traffic).  The two loads of a head (u, v) for BOTH tensors are issued
-// before anything is computed.
+// (a few hundred instructions against kilobytes of traffic).  The loads of a head (u, v) for BOTH tensors are issued
+// before anything is computed.  (Measured and dropped: issuing the first head's loads before the powf / sincosf chain
+// plus a register prefetch of the next head -- 13.5 -> 17.8 us on the decoder shape, the extra live registers cost
+// more occupancy than the overlap bought.)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 rope2d_kernel(T* __restrict__ tokens, T* __restrict__ tokens2, const int64_t* __restrict__ pos, int64_t n_tokens, int N,
@@ -60,16 +62,6 @@ rope2d_kernel(T* __restrict__ tokens, T* __restrict__ tokens2, const int64_t* __
   const int X = r / per_half;            // 0: y half, 1: x half
   const int i0 = (r - X * per_half) * VEC;
   const int64_t b = tok / N, n = tok - b * N;
-  typedef Pack<T, VEC> PK;
-  const int h0 = blockIdx.y * hpt, h1 = min(H, h0 + hpt);
-  const int64_t off = b * sb + n * sn + (int64_t)h0 * D + X * 2 * Q + i0;
-  T* row = tokens + off;
-  T* row2 = tokens2 ? tokens2 + off : nullptr;
-  // the first head's loads go out BEFORE the position load and the powf / sincosf chain, so that the transcendental
-  // work (a few hundred cycles) overlaps the first trip to HBM instead of preceding it
-  PK u = *reinterpret_cast<const PK*>(row), v = *reinterpret_cast<const PK*>(row + Q);
-  PK u2 = u, v2 = v;
-  if (row2) { u2 = *reinterpret_cast<const PK*>(row2); v2 = *reinterpret_cast<const PK*>(row2 + Q); }
   const int p = (int)pos[tok * 2 + X];
   float cs[VEC], sn_[VEC];
 #pragma unroll
@@ -77,28 +69,36 @@ rope2d_kernel(T* __restrict__ tokens, T* __restrict__ tokens2, const int64_t* __
     const float ang = fwd * p / powf(base, (float)(i0 + k) / (float)Q);
     sincosf(ang, &sn_[k], &cs[k]);
   }
-  auto rot = [&](const PK& a, const PK& c, T* dst) {
+  typedef Pack<T, VEC> PK;
+  const int h0 = blockIdx.y * hpt, h1 = min(H, h0 + hpt);
+  const int64_t off = b * sb + n * sn + (int64_t)h0 * D + X * 2 * Q + i0;
+  T* row = tokens + off;
+  T* row2 = tokens2 ? tokens2 + off : nullptr;
+  auto rot = [&](const PK& u, const PK& v, T* dst) {
     PK uo, vo;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const float uf = Cvt<T>::ld(a.v[k]), vf = Cvt<T>::ld(c.v[k]);
+      const float uf = Cvt<T>::ld(u.v[k]), vf = Cvt<T>::ld(v.v[k]);
       uo.v[k] = Cvt<T>::st(uf * cs[k] - vf * sn_[k]);
       vo.v[k] = Cvt<T>::st(vf * cs[k] + uf * sn_[k]);
     }
     *reinterpret_cast<PK*>(dst) = uo;
     *reinterpret_cast<PK*>(dst + Q) = vo;
   };
-  for (int h = h0; h < h1; ++h) {
-    // next head's loads in flight while this head is rotated and stored
-    PK nu = u, nv = v, nu2 = u2, nv2 = v2;
-    if (h + 1 < h1) {
-      nu = *reinterpret_cast<const PK*>(row + D); nv = *reinterpret_cast<const PK*>(row + D + Q);
-      if (row2) { nu2 = *reinterpret_cast<const PK*>(row2 + D); nv2 = *reinterpret_cast<const PK*>(row2 + D + Q); }
+  if (row2) {
+#pragma unroll 2
+    for (int h = h0; h < h1; ++h, row += D, row2 += D) {
+      const PK u = *reinterpret_cast<const PK*>(row), v = *reinterpret_cast<const PK*>(row + Q);
+      const PK u2 = *reinterpret_cast<const PK*>(row2), v2 = *reinterpret_cast<const PK*>(row2 + Q);
+      rot(u, v, row);
+      rot(u2, v2, row2);
     }
-    rot(u, v, row);
-    if (row2) { rot(u2, v2, row2); row2 += D; }
-    row += D;
-    u = nu; v = nv; u2 = nu2; v2 = nv2;
+  } else {
+#pragma unroll 4
+    for (int h = h0; h < h1; ++h, row += D) {
+      const PK u = *reinterpret_cast<const PK*>(row), v = *reinterpret_cast<const PK*>(row + Q);
+      rot(u, v, row);
+    }
   }
 }
 
@@ -120,9 +120,9 @@ static cudaError_t launch_t(void* tokens, void* tokens2, const int64_t* pos, int
   if (n_tokens == 0 || H == 0) return cudaSuccess;
   const int64_t threads = n_tokens * 2 * (Q / vec);
   // heads per thread: all of them when the (token, frequency) threads alone fill the machine several times over,
-  // otherwise fewer, down to 1, until about 600 k threads (148 SMs x 2048 x 2) are in flight
-  int hpt = H;
-  while (hpt > 1 && threads * ((H + hpt - 1) / hpt) < 600000) hpt = (hpt + 1) / 2;
+  // otherwise fewer, down to 2, until about 600 k threads (148 SMs x 2048 x 2) are in flight
+  int hpt = H;     // (1 head per thread measured slower than 2: 14.4 vs 13.1 us on the decoder shape)
+  while (hpt > 2 && threads * ((H + hpt - 1) / hpt) < 600000) hpt = (hpt + 1) / 2;
   dim3 grid((unsigned)((threads + 255) / 256), (unsigned)((H + hpt - 1) / hpt));
   if (vec == 8)
     rope2d_kernel<T, (sizeof(T) >= 4 ? 4 : 8)><<<grid, 256, 0, s>>>((T*)tokens, (T*)tokens2, pos, n_tokens, N, H, D, hpt, sb, sn, base, fwd);

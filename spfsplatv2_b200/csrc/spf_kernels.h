@@ -110,10 +110,11 @@ cudaError_t launch_image_mse(const float* pred, const float* target, int n_image
 cudaError_t launch_multimem_allreduce_f32(float* mc, int64_t numel, int rank, int world, int n_blocks, cudaStream_t s);
 cudaError_t launch_multimem_allreduce_f32_fused(float* mc, int64_t numel, int rank, int world, int n_blocks,
                                                 uint32_t* const* signal_pads, int pad_word_offset, cudaStream_t s);
-cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, float* scales, float* rots, float* sh,
-                                   cudaStream_t s);
+cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, int dens, float exponent, float* scales,
+                                   float* rots, float* sh, float* opac, cudaStream_t s);
 cudaError_t launch_adapter_backward(const float* raw, const float* d_scales, const float* d_rots, const float* d_sh,
-                                    int64_t n, int K, float eps, float* d_raw, cudaStream_t s);
+                                    const float* d_opac, int64_t n, int K, float eps, int dens, float exponent, float* d_raw,
+                                    cudaStream_t s);
 cudaError_t launch_rope2d(void* tokens, void* tokens2, const int64_t* pos, int B, int N, int H, int D, int64_t sb,
                           int64_t sn, int dtype, float base, float fwd, cudaStream_t s);
 

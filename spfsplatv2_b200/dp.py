@@ -94,9 +94,13 @@ class GradAllReduce:
         self.nvls_blocks = int(os.environ.get("SPF_NVLS_BLOCKS", nvls_blocks or 16))
         self._symm: Dict[int, tuple] = {}      # data_ptr -> (tensor, symmetric-memory handle)
         self.nvls_error: Optional[str] = None  # why "auto" fell back to nccl, if it did
-        # cross-rank barriers inside the multimem kernel (signal pads) instead of two barrier launches around it;
-        # switched off (for every bucket, on every rank together) if the collective self-test fails with it
-        self.fused_barrier = os.environ.get("SPF_NVLS_FUSED_BARRIER", "1") != "0"
+        # SPF_NVLS_FUSED_BARRIER=1: cross-rank barriers INSIDE the multimem kernel (signal pads) instead of two barrier
+        # launches around it.  Correct (sums verified at N=2), but measured slower next to the renderer: while a rank
+        # waits for a late peer, all 16 CTAs x 1024 threads of the reduction sit resident on their SMs, where the
+        # stand-alone barrier kernel parks one small CTA (2 GPUs, no step dependency: 37.9 k vs 40.0 k views/s,
+        # profiles/r2_nvls_barrier_ab.md).  Default: separate barrier launches.  Switched off for every bucket, on every
+        # rank together, if the collective self-test fails with it.
+        self.fused_barrier = os.environ.get("SPF_NVLS_FUSED_BARRIER", "0") == "1"
 
     # ---- symmetric-memory buckets (NVLS path) ----------------------------------------------------------------
     def alloc(self, numel: int, dtype: torch.dtype = torch.float32) -> Tensor:

@@ -272,10 +272,38 @@ def make_adapter():
     out = ad.forward(means, opac, raw)
     ws, wr, wh = torch.randn(b, n, 3, generator=g), torch.randn(b, n, 4, generator=g), torch.randn(b, n, 3, 25, generator=g)
     ((out.scales * ws).sum() + (out.rotations * wr).sum() + (out.harmonics * wh).sum()).backward()
+    extra = {}
+    # The encoder's opacity mapping (EncoderSPFSplatV2.map_pdf_to_opacity, encoder_spfsplatv2.py:146-159) run from the
+    # reference file itself: the method is lifted out of the class by its AST (importing the module would pull in the whole
+    # backbone) and called on a stand-in `self` that only carries cfg.opacity_mapping.  Then the head post-processing
+    # of :255-268: densities = sigmoid(channel 0) -> opacities; the rest -> the adapter.
+    import ast
+    import textwrap
+    src = open(os.path.join(REF, "src/model/encoder/encoder_spfsplatv2.py")).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "map_pdf_to_opacity")
+    fn.returns = None
+    for a in fn.args.args:
+        a.annotation = None
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "encoder_spfsplatv2.py", "exec"), ns)
+    map_pdf = ns["map_pdf_to_opacity"]
+    for tag, (initial, final, warm_up, step) in {"e1": (0.0, 0.0, 1, 0), "warm": (0.0, 3.0, 1000, 500)}.items():
+        fake = types.SimpleNamespace(cfg=types.SimpleNamespace(opacity_mapping=types.SimpleNamespace(initial=initial, final=final, warm_up=warm_up)))
+        head = torch.randn(b, n, 83, generator=g)
+        head[..., 1:] = raw.detach()
+        head = head.requires_grad_()
+        dens = head[..., 0].sigmoid()
+        op = map_pdf(fake, dens, step)
+        o2 = ad.forward(means, op, head[..., 1:])
+        wo = torch.randn(b, n, generator=g)
+        ((o2.opacities * wo).sum() + (o2.scales * ws).sum() + (o2.rotations * wr).sum() + (o2.harmonics * wh).sum()).backward()
+        extra.update({f"head_{tag}": head.detach().numpy(), f"head_{tag}_cfg": np.array([initial, final, warm_up, step], dtype=np.float64),
+                      f"head_{tag}_opacities": op.detach().numpy(), f"head_{tag}_wo": wo.numpy(), f"head_{tag}_d": head.grad.numpy()})
+        print(f"head {tag}: opacity range {op.min().item():.4f}..{op.max().item():.4f}")
     np.savez_compressed(os.path.join(HERE, "adapter_ref.npz"), raw=raw.detach().numpy(), means=means.numpy(), opacities=opac.numpy(),
                         scales=out.scales.detach().numpy(), rotations=out.rotations.detach().numpy(),
                         harmonics=out.harmonics.detach().numpy(), ws=ws.numpy(), wr=wr.numpy(), wh=wh.numpy(),
-                        d_raw=raw.grad.numpy(), sh_mask=ad.sh_mask.numpy())
+                        d_raw=raw.grad.numpy(), sh_mask=ad.sh_mask.numpy(), **extra)
     print(f"adapter: scales max {out.scales.max().item():.3f}, d_raw norm {raw.grad.norm().item():.3f}")
 
 

@@ -269,3 +269,28 @@ def test_fused_adapter_matches_reference_adapter_golden():
     o = dec(gs, ext, K, torch.full((b, 1), 0.5, device=D0), torch.full((b, 1), 100.0, device=D0), (32, 32))
     o.color.mean().backward()
     assert torch.isfinite(o.color).all()
+
+
+@pytest.mark.parametrize("tag", ["e1", "warm"])
+def test_fused_head_opacity_mapping_matches_reference_golden(tag):
+    """UnifiedGaussianAdapter.forward_head -- density sigmoid + EncoderSPFSplatV2.map_pdf_to_opacity
+    (encoder_spfsplatv2.py:146-159) + the adapter (gaussian_adapter.py:122-150) in one kernel -- against the outputs and
+    d/d(head output) of the reference's own functions (fixture: tests/golden/make_golden.py:make_adapter), for the shipped
+    schedule (exponent 1) and a mid-warm-up exponent (2^1.5)."""
+    from spfsplatv2_b200.adapter import GaussianAdapterCfg, OpacityMappingCfg, UnifiedGaussianAdapter
+    g = np.load(os.path.join(GOLD, "adapter_ref.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(D0)
+    initial, final, warm_up, step = [float(x) for x in g[f"head_{tag}_cfg"]]
+    ad = UnifiedGaussianAdapter(GaussianAdapterCfg(0.5, 15.0, 4))
+    head = t(f"head_{tag}").requires_grad_()
+    out = ad.forward_head(t("means"), head, OpacityMappingCfg(initial, final, int(warm_up)), int(step))
+    assert out.opacities.shape == g["opacities"].shape
+    assert torch.allclose(out.opacities, t(f"head_{tag}_opacities"), rtol=3e-6, atol=1e-7)
+    assert torch.allclose(out.scales, t("scales"), rtol=2e-6, atol=1e-9) and torch.equal(out.harmonics, t("harmonics"))
+    ((out.opacities * t(f"head_{tag}_wo")).sum() + (out.scales * t("ws")).sum() + (out.rotations * t("wr")).sum() +
+     (out.harmonics * t("wh")).sum()).backward()
+    want = t(f"head_{tag}_d")
+    assert torch.allclose(head.grad[..., 0], want[..., 0], rtol=2e-5, atol=1e-8)             # density logit
+    assert torch.allclose(head.grad[..., 1:4], want[..., 1:4], rtol=1e-5, atol=1e-9)
+    assert torch.allclose(head.grad[..., 4:8], want[..., 4:8], rtol=2e-5, atol=2e-6)
+    assert torch.allclose(head.grad[..., 8:], want[..., 8:], rtol=1e-6, atol=0)
