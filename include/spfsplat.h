@@ -241,7 +241,7 @@ SPF_API int spf_rope2d_qk(void* q, void* k, const int64_t* positions, int32_t B,
 /* In-switch (NVLS multicast) sum all-reduce of one fp32 gradient bucket, in place.  Replaces the NCCL all-reduce torch DDP
  * issues for the replicated parameters' gradients (src/main.py:141-145).  multicast_bucket: the MULTICAST address of a
  * symmetric-memory bucket of numel floats (numel % 4 == 0, 16-byte aligned), bound on all `world` ranks; this rank reduces
- * and re-broadcasts slice `rank` of `world`.  n_blocks: CTAs to spend (1..148).  The caller orders the launch between two
+ * and re-broadcasts slice `rank` of `world`.  n_blocks: CTAs to spend.  The caller orders the launch between two
  * cross-rank barriers on the same stream (every bucket final before; every slice broadcast after). */
 SPF_API int spf_multimem_allreduce_f32(float* multicast_bucket, int64_t numel, int32_t rank, int32_t world, int32_t n_blocks,
                                void* stream);

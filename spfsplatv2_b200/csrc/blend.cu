@@ -1180,7 +1180,7 @@ cudaError_t launch_blend_backward(const Dims& d, const SpfRasterIn& in, const Sp
     if (e0 != cudaSuccess) return e0;
   }
   const size_t smem = sizeof(BwdSmem);
-  const int grid2 = use_log ? min(grid, 148 * 3) : grid;   // fallback-only launch: one wave of resident CTAs
+  const int grid2 = use_log ? min(grid, sm_count() * 3) : grid;   // fallback-only launch: one wave of resident CTAs
   cudaError_t e;
   if (d.flags & SPF_FLAG_NO_TMA) {
     e = cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -4,11 +4,25 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "spf_kernels.h"
 #include "spf_math.h"
 
 namespace {
 thread_local char g_err[512] = "";
+
+// SPF_NVTX=1: one NVTX range per launch stage (spf/project_forward, spf/scan, ... spf/pose_reduce) around the host-side
+// enqueue, so nsys / ncu --nvtx timelines show the stages by name; off by default (no overhead).
+bool nvtx_on() {
+  static const bool on = [] { const char* e = getenv("SPF_NVTX"); return e && e[0] == '1'; }();
+  return on;
+}
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_on()) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -122,11 +136,16 @@ int spf_raster_forward_stages(const SpfRasterDesc* desc, const SpfRasterIn* in, 
   cudaError_t e;
   if ((mask & 1u) && (e = cudaMemsetAsync(st->control, 0, (size_t)cl.total * sizeof(int32_t), s)) != cudaSuccess)
     return cuda_fail(e, "memset(control)");
-  if ((mask & 2u) && (e = spf::launch_project_forward(d, *in, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "project_forward");
-  if ((mask & 4u) && (e = spf::launch_scan(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "scan");
-  if ((mask & 8u) && (e = spf::launch_emit(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "emit");
-  if ((mask & 16u) && (e = spf::launch_tile_sort_pack(d, *st, cl, s)) != cudaSuccess) return cuda_fail(e, "tile_sort_pack");
-  if ((mask & 32u) && (e = spf::launch_blend_forward(d, *in, *st, *out, s)) != cudaSuccess) return cuda_fail(e, "blend_forward");
+#define SPF_STAGE(bit, name, call)                                   \
+  if (mask & (bit)) {                                                \
+    NvtxRange r_("spf/" name);                                       \
+    if ((e = (call)) != cudaSuccess) return cuda_fail(e, name);      \
+  }
+  SPF_STAGE(2u, "project_forward", spf::launch_project_forward(d, *in, *st, cl, s))
+  SPF_STAGE(4u, "scan", spf::launch_scan(d, *st, cl, s))
+  SPF_STAGE(8u, "emit", spf::launch_emit(d, *st, cl, s))
+  SPF_STAGE(16u, "tile_sort_pack", spf::launch_tile_sort_pack(d, *st, cl, s))
+  SPF_STAGE(32u, "blend_forward", spf::launch_blend_forward(d, *in, *st, *out, s))
   g_err[0] = 0;
   return SPF_OK;
 }
@@ -151,9 +170,9 @@ int spf_raster_backward_stages(const SpfRasterDesc* desc, const SpfRasterIn* in,
   make_dims(desc, in->sh_coeffs, in->shs != nullptr, d);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if ((mask & 1u) && (e = spf::launch_blend_backward(d, *in, *st, *gout, *gin, s)) != cudaSuccess) return cuda_fail(e, "blend_backward");
-  if ((mask & 2u) && (e = spf::launch_project_backward(d, *in, *st, *gin, s)) != cudaSuccess) return cuda_fail(e, "project_backward");
-  if ((mask & 4u) && (e = spf::launch_pose_reduce(d, *in, *gin, s)) != cudaSuccess) return cuda_fail(e, "pose_reduce");
+  SPF_STAGE(1u, "blend_backward", spf::launch_blend_backward(d, *in, *st, *gout, *gin, s))
+  SPF_STAGE(2u, "project_backward", spf::launch_project_backward(d, *in, *st, *gin, s))
+  SPF_STAGE(4u, "pose_reduce", spf::launch_pose_reduce(d, *in, *gin, s))
   g_err[0] = 0;
   return SPF_OK;
 }
@@ -262,7 +281,7 @@ int spf_multimem_allreduce_f32(float* multicast_bucket, int64_t numel, int32_t r
   if ((reinterpret_cast<uintptr_t>(multicast_bucket) & 15) != 0 || numel < 0 || (numel & 3) != 0)
     return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: bucket must be 16-byte aligned with numel % 4 == 0");
   if (world < 1 || rank < 0 || rank >= world) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: bad rank / world");
-  if (n_blocks < 1 || n_blocks > 148) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: n_blocks must be 1..148");
+  if (n_blocks < 1 || n_blocks > 1024) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: n_blocks must be 1..1024");
   cudaError_t e = spf::launch_multimem_allreduce_f32(multicast_bucket, numel, rank, world, n_blocks,
                                                      static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "multimem_allreduce_f32");
@@ -275,7 +294,7 @@ int spf_multimem_allreduce_f32_fused(float* multicast_bucket, int64_t numel, int
   if (numel < 0 || (numel & 3) || (reinterpret_cast<uintptr_t>(multicast_bucket) & 15))
     return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: bucket must be 16-byte aligned with numel % 4 == 0");
   if (world < 1 || world > 1024 || rank < 0 || rank >= world) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: bad rank / world");
-  if (n_blocks < 1 || n_blocks > 148) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: n_blocks must be 1..148");
+  if (n_blocks < 1 || n_blocks > spf::sm_count()) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32_fused: n_blocks must be 1..#SMs (the CTAs of all ranks must be co-resident)");
   if (pad_word_offset < 0 || (int64_t)pad_word_offset + 2LL * n_blocks * world > pad_words)
     return fail(SPF_ERR_WORKSPACE, "spf_multimem_allreduce_f32_fused: signal pad too small for 2 * n_blocks * world flags");
   cudaError_t e = spf::launch_multimem_allreduce_f32_fused(multicast_bucket, numel, rank, world, n_blocks,

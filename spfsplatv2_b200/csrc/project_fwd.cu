@@ -288,7 +288,7 @@ cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const S
     cudaError_t e = cudaFuncSetAttribute(project_forward_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(PFSmem));
     if (e != cudaSuccess) return e;
-    const int grid1 = min(d.B * d.NB, 2 * 148);
+    const int grid1 = min(d.B * d.NB, 2 * sm_count());
     pdl_launch(project_forward_stream_kernel, grid1, 2 * PROJ_THREADS, sizeof(PFSmem), s)(d, in, st, st.control + cl.tile_count,
                                                                              st.control + cl.block_sum);
     return cudaGetLastError();

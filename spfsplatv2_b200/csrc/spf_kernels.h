@@ -58,6 +58,19 @@ inline bool pdl_enabled() {
   return on;
 }
 
+// Number of SMs of the current device (148 on B200), read once per device; sizes the persistent / grid-stride launches.
+inline int sm_count() {
+  static thread_local int cached_dev = -1, cached_sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached_sms;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached_sms = n;
+    cached_dev = dev;
+  }
+  return cached_sms;
+}
+
 template <typename K>
 struct PdlLaunch {
   K kernel;
