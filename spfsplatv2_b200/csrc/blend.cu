@@ -178,6 +178,7 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   bool done = !inside;
   unsigned donemask = __ballot_sync(FULL, done);
   bool queued = false;   // warp-uniform: some queue is non-empty
+  int pass0 = 0;         // first record of the current pass (the queues hold tile-list indices)
 
   // phase B: every pixel composites its queued pairs in list order
   auto drain = [&]() {
@@ -190,7 +191,7 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
       const bool act = (i < n) && !done;
       if (act && test_T < T_STOP) done = true;
       if (act && !done) {
-        const float4* r = S.buf + 3u * (en.y & (unsigned)(PASS - 1));
+        const float4* r = S.buf + 3u * (en.y - (unsigned)pass0);
         const float2 c01 = *reinterpret_cast<const float2*>(&r[1].z);
         const float2 c2d = *reinterpret_cast<const float2*>(&r[2].x);
         const float w = alpha * T;
@@ -231,6 +232,7 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
   const int npass = (L + PASS - 1) / PASS;
   for (int p = 0; p < npass; ++p) {
     const int p0 = p * PASS, pc = min(PASS, L - p0);
+    pass0 = p0;
     // ---- stage the pass's records (one bulk copy) while the block culls
     if (TMA) {
       if (tid == 0) {
@@ -890,8 +892,8 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
 // fixed order: bit-reproducible.  Long tile lists are processed in windows of LOG_W records (each warp's log is sorted
 // by record).  Tiles with an incomplete log or too many multi-region records in a window are left to the recomputing
 // kernel above (flagged through pair_count).
-constexpr int LOG_W = 416;         // records per window of the tile list (staged in shared memory)
-constexpr int LOG_ESLOTS = 640;    // exchange slots per window (one per (multi-region record, overlapped region))
+constexpr int LOG_W = 320;         // records per window of the tile list (staged in shared memory)
+constexpr int LOG_ESLOTS = 448;    // exchange slots per window (one per (multi-region record, overlapped region))
 
 struct LogSmem {
   float4 rec[LOG_W * 3];                 // the window's slab records
@@ -906,7 +908,7 @@ struct LogSmem {
   int base;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+__global__ void __launch_bounds__(TILE_THREADS, 5)
 blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                           float* __restrict__ dup_grad) {
   pdl_enter();
@@ -988,12 +990,16 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
       unsigned mask = 0u;
       if (r < wn) {
         const float4 bb = __ldg(cull + w0 + r);
+        float f0, f1, f2, f3;
+        if (region_rect(bb, (float)tx0, (float)min(tx0 + TILE - 1, d.W - 1), (float)ty0, (float)min(ty0 + TILE - 1, d.H - 1), f0, f1,
+                        f2, f3)) {
+          // tile-local pixel rectangle, intersected with the eight regions in integers (as the forward's cull does)
+          const int X0 = (int)f0 - tx0, X1 = (int)f1 - tx0, Y0 = (int)f2 - ty0, Y1 = (int)f3 - ty0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const int rx = tx0 + (w & 1) * 8, ry = ty0 + (w >> 1) * 4;
-          float f0, f1, f2, f3;
-          if (region_rect(bb, (float)rx, (float)min(rx + 7, d.W - 1), (float)ry, (float)min(ry + 3, d.H - 1), f0, f1, f2, f3))
-            mask |= 1u << w;
+          for (int w = 0; w < 8; ++w) {
+            const int hx = (w & 1) * 8, hy = (w >> 1) * 4;
+            if ((max(X0, hx) <= min(X1, hx + 7)) && (max(Y0, hy) <= min(Y1, hy + 3))) mask |= 1u << w;
+          }
         }
       }
       const int nreg = __popc(mask);
@@ -1010,6 +1016,27 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
       if (tid == 0) { st.pair_count[(size_t)t * 8] = -1; st.control[3] = 1; }
       return;
     }
+
+    // a finished run (this warp's sums for window record jl): straight to the duplicate's slot if the record touches
+    // no other region, else into this region's exchange slot
+    auto emit_run = [&](int jl, const float* v) {
+      const unsigned info = S.info[jl];
+      const unsigned mask = info & 0xffu;
+      if (__popc(mask) <= 1) {
+        const int slot = __float_as_int(S.rec[3 * jl + 2].z);
+        if ((int64_t)slot < d.cap) {
+          float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
+        }
+        atomicOr(&S.wrote[jl >> 5], 1u << (jl & 31));
+      } else {
+        float* ex = S.exch[(info >> 8) + __popc(mask & ((1u << wid) - 1u))];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) ex[k] = v[k];
+      }
+    };
 
     // ---- this warp's pairs whose record lies in the window
     while (bi < nbatch) {
@@ -1028,8 +1055,6 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
       float v[10];
 #pragma unroll
       for (int k = 0; k < 10; ++k) v[k] = 0.0f;
-      int slot = 0;
-      if (inwin) slot = __float_as_int(S.rec[3 * j + 2].z);
       if (am) {
         // keyed scan: (T_before, P_after) of every live pair
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, cc = a, g = a;
@@ -1090,47 +1115,48 @@ blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterSta
       }
       const int jprev = __shfl_up_sync(FULL, j, 1);
       const bool head = (j >= 0) && (lane == 0 || jprev != j);
-      if (carry_j >= 0) {                      // first part of lane 0's run, parked by the previous batch
-        if (lane == 0 && inwin && jraw == carry_j) {
+      // The LAST run of a batch may continue in the next batch, so it is never emitted at once: its sums are parked
+      // (carry) and either merged into lane 0's run of the next batch (same record) or emitted from there (no load of
+      // the next entry is needed to find out which).
+      const int j0 = __shfl_sync(FULL, j, 0);
+      if (carry_j >= 0) {
+        if (j0 == carry_j) {                   // lane 0's run is the continuation
+          if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < 10; ++k) v[k] = carry[k] + v[k];
+            for (int k = 0; k < 10; ++k) v[k] = carry[k] + v[k];
+          }
+        } else if (lane == 0) {                // the parked run was complete
+          float cv[10];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) cv[k] = carry[k];
+          emit_run(carry_j, cv);
         }
         carry_j = -1;
         __syncwarp();
       }
-      // does the last run continue in the next batch?  (lane 31 peeks at the next entry)
-      int cont = 0;
-      if (lane == 31 && inwin && idx + 1 < count) cont = ((int)(lp[idx + 1].x & PAIR_J_MASK) == jraw) ? 1 : 0;
-      cont = __shfl_sync(FULL, cont, 31);
       const unsigned hm = __ballot_sync(FULL, head);
       const int hlast = hm ? 31 - __clz(hm) : -1;
-      if (cont) {
+      if (head) {
         if (lane == hlast) {
 #pragma unroll
           for (int k = 0; k < 10; ++k) carry[k] = v[k];
-        }
-        carry_j = __shfl_sync(FULL, jraw, 31);
-        __syncwarp();
-      }
-      if (head && !(cont && lane == hlast)) {          // run head: holds this warp's sums for record j
-        const unsigned info = S.info[j];
-        const unsigned mask = info & 0xffu;
-        if (__popc(mask) <= 1) {
-          if ((int64_t)slot < d.cap) {
-            float4* dst = reinterpret_cast<float4*>(dup_grad + (size_t)slot * 12);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            *reinterpret_cast<float2*>(dst + 2) = make_float2(v[8], v[9]);
-          }
-          atomicOr(&S.wrote[j >> 5], 1u << (j & 31));
         } else {
-          float* ex = S.exch[(info >> 8) + __popc(mask & ((1u << wid) - 1u))];
-#pragma unroll
-          for (int k = 0; k < 10; ++k) ex[k] = v[k];
+          emit_run(j, v);
         }
       }
+      if (hm) carry_j = __shfl_sync(FULL, j, hlast);
+      __syncwarp();
       if (bym) break;                      // the rest of this batch belongs to a later window: revisit it there
       ++bi;
+    }
+    if (carry_j >= 0) {                    // the window's (or the log's) last run
+      if (lane == 0) {
+        float cv[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) cv[k] = carry[k];
+        emit_run(carry_j, cv);
+      }
+      carry_j = -1;
     }
     __syncthreads();
     // ---- window epilogue: multi-region records: add the regions' sums in region order; untouched single-region
