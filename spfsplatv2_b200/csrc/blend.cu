@@ -892,8 +892,8 @@ blend_backward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState s
 // fixed order: bit-reproducible.  Long tile lists are processed in windows of LOG_W records (each warp's log is sorted
 // by record).  Tiles with an incomplete log or too many multi-region records in a window are left to the recomputing
 // kernel above (flagged through pair_count).
-constexpr int LOG_W = 320;         // records per window of the tile list (staged in shared memory)
-constexpr int LOG_ESLOTS = 448;    // exchange slots per window (one per (multi-region record, overlapped region))
+constexpr int LOG_W = 256;         // records per window of the tile list (staged in shared memory)
+constexpr int LOG_ESLOTS = 320;    // exchange slots per window (one per (multi-region record, overlapped region))
 
 struct LogSmem {
   float4 rec[LOG_W * 3];                 // the window's slab records
@@ -908,7 +908,7 @@ struct LogSmem {
   int base;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 5)
+__global__ void __launch_bounds__(TILE_THREADS, 6)
 blend_backward_log_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st, SpfRasterGradOut go,
                           float* __restrict__ dup_grad) {
   pdl_enter();
