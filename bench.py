@@ -379,7 +379,7 @@ def run_ours(args):
         top = max((k for k in st if k in algo), key=lambda k: st[k])
         traffic = None
         try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             if tj.get("workload") == args.workload:
                 traffic = tj["kernels"].get(top, {}).get("dram_bytes_per_launch")
         except Exception:
