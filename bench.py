@@ -206,14 +206,18 @@ def run_ours(args):
         if world > 1 and ar_state["dep"] == "lag1":
             torch.cuda.current_stream(dev).wait_event(ar_done[ar_state["k"] % 2])
 
+    SENT = 4096        # sentinel elements refreshed every step; the rest of the bucket stays zero under summation
+
     def ar_launch():
-        """The step's replicated-parameter gradient: every rank writes rank+1 into the bucket (stand-in for the
-        backward's stores), then ONE sum all-reduce on the side stream.  Checked after the timed loop."""
+        """The step's replicated-parameter gradient: ONE sum all-reduce of the whole 64 MiB bucket on the side stream.
+        The backward's stores into the bucket are stood in for by rank+1 written into its first SENT elements (the rest
+        is zero, and stays zero when summed), so every step's reduction can be verified after the timed loop without a
+        64 MiB fill kernel per step on the critical path."""
         if world == 1:
             return
         k = ar_state["k"]
         buf = ar_bufs[k % 2]
-        buf.fill_(float(rank + 1))
+        buf[:SENT].fill_(float(rank + 1))
         reducer.launch([buf])
         ar_done[k % 2].record(reducer.stream)
         ar_state["k"] = k + 1
@@ -223,9 +227,10 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         want = float(world * (world + 1) // 2)
         for i, buf in enumerate(ar_bufs):
-            if ar_state["k"] > i and not bool((buf == want).all()):
-                raise RuntimeError(f"gradient all-reduce gave wrong sums in bucket {i}: expected {want} everywhere, "
-                                   f"got min {float(buf.min())} max {float(buf.max())}")
+            if ar_state["k"] > i and not (bool((buf[:SENT] == want).all()) and bool((buf[SENT:] == 0).all())):
+                raise RuntimeError(f"gradient all-reduce gave wrong sums in bucket {i}: expected {want} in the first {SENT} "
+                                   f"elements and 0 elsewhere, got head min {float(buf[:SENT].min())} max {float(buf[:SENT].max())}, "
+                                   f"tail absmax {float(buf[SENT:].abs().max())}")
 
     def step_resident():
         ar_begin()
