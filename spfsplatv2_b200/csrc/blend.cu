@@ -126,6 +126,7 @@ struct FwdSmem {
   int qcnt[8][32];               // per warp: queued pairs per pixel
   float2 pixf[8][32];            // per warp: pixel coordinates of the region's 32 pixel lanes
   int wcnt[8][8], woff[8][8];    // [region][warp]: hits found by a warp in the current cull round / their offsets
+  unsigned bal[8][8];            // [region][warp]: the warp's hit ballot of the current cull round
   int hbase[8];                  // per region: hits so far in this pass
   uint8_t rowcol[8][32];         // [width-1][k] -> lane offset (row * 8 + column) of candidate k of a hit
   uint64_t bar;
@@ -255,15 +256,18 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
           X0 = (int)f0 - tx0; X1 = (int)f1 - tx0; Y0 = (int)f2 - ty0; Y1 = (int)f3 - ty0;
         }
       }
-      unsigned bal[8];
+      // regions touched: columns X0>>3 .. X1>>3 (of 2), bands Y0>>2 .. Y1>>2 (of 4); region w = band * 2 + column
       unsigned mask = 0u;
+      if (X0 <= X1) {
+        const unsigned cols = (X0 < 8 ? 1u : 0u) | (X1 >= 8 ? 2u : 0u);
+        const unsigned bands = ((2u << (Y1 >> 2)) - 1u) & ~((1u << (Y0 >> 2)) - 1u);
+        mask = ((bands & 1u) ? cols : 0u) | ((bands & 2u) ? cols << 2 : 0u) | ((bands & 4u) ? cols << 4 : 0u) |
+               ((bands & 8u) ? cols << 6 : 0u);
+      }
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
-        const int hx = (w & 1) * 8, hy = (w >> 1) * 4;
-        const bool hit = (max(X0, hx) <= min(X1, hx + 7)) && (max(Y0, hy) <= min(Y1, hy + 3));
-        bal[w] = __ballot_sync(FULL, hit);
-        if (hit) mask |= 1u << w;
-        if (lane == w) S.wcnt[w][wid] = __popc(bal[w]);
+        const unsigned bal = __ballot_sync(FULL, (mask >> w) & 1u);
+        if (lane == w) { S.bal[w][wid] = bal; S.wcnt[w][wid] = __popc(bal); }
       }
       __syncthreads();
       if (tid < 64) {
@@ -278,16 +282,14 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
         S.woff[w][wp] = off;
       }
       __syncthreads();
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        if (mask & (1u << w)) {
-          const int hx = (w & 1) * 8, hy = (w >> 1) * 4;
-          const int xa = max(X0, hx), xb = min(X1, hx + 7), ya = max(Y0, hy), yb = min(Y1, hy + 3);
-          const int pos = S.woff[w][wid] + __popc(bal[w] & lt_mask);
-          if (pos < HCAP)
-            S.hit[w][pos] = (unsigned)i | ((unsigned)((ya - hy) * 8 + (xa - hx)) << 9) | ((unsigned)(xb - xa) << 14) |
-                            ((unsigned)(yb - ya) << 17);
-        }
+      for (unsigned m = mask; m; m &= m - 1) {      // 1.2 regions per record on average
+        const int w = __ffs(m) - 1;
+        const int hx = (w & 1) * 8, hy = (w >> 1) * 4;
+        const int xa = max(X0, hx), xb = min(X1, hx + 7), ya = max(Y0, hy), yb = min(Y1, hy + 3);
+        const int pos = S.woff[w][wid] + __popc(S.bal[w][wid] & lt_mask);
+        if (pos < HCAP)
+          S.hit[w][pos] = (unsigned)i | ((unsigned)((ya - hy) * 8 + (xa - hx)) << 9) | ((unsigned)(xb - xa) << 14) |
+                          ((unsigned)(yb - ya) << 17);
       }
     }
     if (tid < 64 && (tid & 7) == 0) S.hbase[tid >> 3] = hrun;
