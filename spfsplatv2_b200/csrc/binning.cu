@@ -375,6 +375,7 @@ cudaError_t launch_tile_sort_pack(const Dims& d, const SpfRasterState& st, const
   // duplicate count (about 1.5 x N), so cap / tiles over-estimates the mean list; about twice the mean covers the
   // spread between tiles (longer lists still work: in-place global sort)
   const int64_t want = 4 * d.cap / (3 * (int64_t)d.B * d.T);   // cap ~ 1.5 x N  ->  ~2 x the mean list length
+  if (want <= 1024) return launch_tsp<1024, 1024>(d, st, cl, s);     // 12 KB
   if (want <= 2048) return launch_tsp<2048, 2048>(d, st, cl, s);     // 24 KB
   if (want <= 4096) return launch_tsp<4096, 4096>(d, st, cl, s);     // 48 KB
   return launch_tsp<8192, 8192>(d, st, cl, s);                       // 96 KB

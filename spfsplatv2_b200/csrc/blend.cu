@@ -291,6 +291,7 @@ blend_forward_kernel(Dims d, const float* __restrict__ bg_all, SpfRasterState st
           S.hit[w][pos] = (unsigned)i | ((unsigned)((ya - hy) * 8 + (xa - hx)) << 9) | ((unsigned)(xb - xa) << 14) |
                           ((unsigned)(yb - ya) << 17);
       }
+      __syncwarp();       // every lane has read this round's ballots before lane w overwrites them in the next round
     }
     if (tid < 64 && (tid & 7) == 0) S.hbase[tid >> 3] = hrun;
     __syncthreads();               // hit lists and counts complete
