@@ -47,9 +47,10 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons (every 20 ms, with timestamps) while the GPU is under load; stop()
-    reports the samples that fall inside the timed region, or -- if the timed region was shorter than the sampling
-    period allows -- those taken over the whole loaded span (warm-up + timed + end-to-end loops), and says which."""
+    """Samples SM clocks and clock-event (throttle) reasons while the GPU is under load, with timestamps; stop() reports
+    the samples that fall inside the timed region.  NVML is polled in-process every 2 ms (the timed region of the default
+    run is ~15 ms: nvidia-smi's fastest loop, 20 ms, would put at most one sample into it); if NVML cannot be loaded,
+    `nvidia-smi -lms 20` is read instead and stop() says which span its samples cover."""
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -57,10 +58,32 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # nvidia-smi fallback: (t, csv line)
+        self.samples = []        # nvml: (t, sm_mhz, reasons bitmask)
         self.window = None
+        self.nvml = None
+        self.max_mhz = None
+        self._stop = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.idx
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.idx])
+                except (ValueError, IndexError):
+                    pass
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
@@ -68,6 +91,20 @@ class ClockSampler:
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    why = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    why = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.time(), float(mhz), int(why)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -77,8 +114,26 @@ class ClockSampler:
         self.window = (t0, t1)
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop = True
+            self.th.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap,
+                     "hw_power_brake": n.nvmlClocksThrottleReasonHwPowerBrakeSlowdown}
+            inside = [x for x in self.samples if self.window and self.window[0] <= x[0] <= self.window[1]]
+            span = "timed region"
+            if len(inside) < 2:
+                inside, span = self.samples, "warm-up + timed + end-to-end loops (timed region shorter than 2 samples)"
+            sm = sorted(x[1] for x in inside)
+            bits = 0
+            for x in inside:
+                bits |= x[2]
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, v in names.items() if bits & v), "samples": len(sm), "window": span,
+                    "source": "nvml, 2 ms period"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -106,7 +161,7 @@ class ClockSampler:
             inside, span = self.lines[1:] if len(self.lines) > 1 else self.lines, "warm-up + timed + end-to-end loops (timed region shorter than 2 samples)"
         sm, mx, reasons = parse(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "window": span}
+                "samples": len(sm), "window": span, "source": "nvidia-smi -lms 20"}
 
 
 def _make_inputs(workload: str, rank: int, pin: bool):
