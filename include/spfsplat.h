@@ -86,6 +86,18 @@ typedef struct {
   const float* bg;           /* [B,3]   settings.bg */
   const float* pre_scale;    /* [B] or NULL: means and scales are multiplied by this before use
                                 (the 1/near scale-invariance step, cuda_splatting.py:66-74) */
+  /* RAW-HEAD INPUT (optional; SURVEY.md 8f rank 2 fused into the projection kernels).  If raw_head is not NULL the
+   * Gaussian parameters are taken straight from the encoder head's output rows and scales / rotations / shs (and, with a
+   * density channel, opacities) above must be NULL: row = [density logit (if raw_has_density), 3 scale logits,
+   * 4 quaternion components, 3 x sh_coeffs SH coefficients ([3][K], the encoder's layout)], mapped inside the kernels
+   * exactly like UnifiedGaussianAdapter (gaussian_adapter.py:122-150) and EncoderSPFSplatV2.map_pdf_to_opacity
+   * (encoder_spfsplatv2.py:146-159,255-268).  Neither the adapter's outputs nor their gradients ever exist in HBM.
+   * Requires n_gaussians % 4 == 0, 16-byte aligned tensors, at most 32 views per call. */
+  const float* raw_head;     /* [S,P,raw_stride] or NULL */
+  int32_t      raw_stride;   /* floats per row = raw_has_density + 7 + 3*sh_coeffs */
+  int32_t      raw_has_density;
+  float        raw_eps;      /* quaternion normalisation eps (1e-8 in the reference) */
+  float        opacity_exponent; /* e = 2^x of map_pdf_to_opacity; 1 for the shipped config */
 } SpfRasterIn;
 
 /* Caller-allocated intermediates.  Forward fills them; backward reads them.
@@ -144,6 +156,8 @@ typedef struct {
   float* dL_dviewmatrix;     /* [B,16] */
   float* dL_dmeans2D;        /* [B,P,3] or NULL: screen-space (NDC) mean gradients, the side channel
                                 of cuda_splatting.py:97-102 */
+  float* dL_draw_head;       /* [S,P,raw_stride]: gradient of the raw head rows; required (and dL_dscales /
+                                dL_drotations / dL_dshs ignored, may be NULL) when in.raw_head is given */
 } SpfRasterGradIn;
 
 SPF_API int         spf_version(void);

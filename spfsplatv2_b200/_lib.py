@@ -30,7 +30,8 @@ class SpfRasterDesc(C.Structure):
 class SpfRasterIn(C.Structure):
     _fields_ = [("means3D", _fp), ("scales", _fp), ("rotations", _fp), ("opacities", _fp), ("shs", _fp),
                 ("colors_precomp", _fp), ("sh_coeffs", C.c_int32), ("viewmatrix", _fp), ("projmatrix", _fp),
-                ("tanfov", _fp), ("bg", _fp), ("pre_scale", _fp)]
+                ("tanfov", _fp), ("bg", _fp), ("pre_scale", _fp), ("raw_head", _fp), ("raw_stride", C.c_int32),
+                ("raw_has_density", C.c_int32), ("raw_eps", C.c_float), ("opacity_exponent", C.c_float)]
 
 
 class SpfRasterState(C.Structure):
@@ -50,7 +51,7 @@ class SpfRasterGradOut(C.Structure):
 class SpfRasterGradIn(C.Structure):
     _fields_ = [("dup_grad", _fp), ("pose_partial", _fp), ("dL_dmeans3D", _fp), ("dL_dscales", _fp),
                 ("dL_drotations", _fp), ("dL_dopacities", _fp), ("dL_dshs", _fp), ("dL_dcolors", _fp),
-                ("dL_dviewmatrix", _fp), ("dL_dmeans2D", _fp)]
+                ("dL_dviewmatrix", _fp), ("dL_dmeans2D", _fp), ("dL_draw_head", _fp)]
 
 
 EXPORTS = ("spf_version", "spf_last_error", "spf_raster_control_ints", "spf_raster_forward",

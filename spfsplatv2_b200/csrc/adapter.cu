@@ -10,6 +10,7 @@
 //     p = sigmoid(raw[0]);  opacity = 0.5 * (1 - (1 - p)^e + p^(1/e)),  e = 2^x  (x from the warm-up schedule, host side)
 // HBM-bound: 2 * (7 + 3K) * 4 bytes per Gaussian each way.  A block stages 128 raw rows in shared memory with coalesced
 // 128-bit loads and writes the three outputs element-parallel (coalesced) -- no per-thread 328-byte strides.
+#include "spf_adapter_math.cuh"
 #include "spf_device.cuh"
 #include "spf_kernels.h"
 
@@ -17,13 +18,6 @@ namespace spf {
 
 constexpr int AD_ROWS = 128;
 constexpr int AD_THREADS = 256;
-
-__device__ __forceinline__ float softplus_t(float x) { return x > 20.0f ? x : log1pf(expf(x)); }   // torch: beta 1, threshold 20
-__device__ __forceinline__ float sh_mask_of(int k) {
-  const int deg = (k >= 16) ? 4 : (k >= 9) ? 3 : (k >= 4) ? 2 : (k >= 1) ? 1 : 0;
-  const float m[5] = {1.0f, 0.1f * 0.25f, 0.1f * 0.0625f, 0.1f * 0.015625f, 0.1f * 0.00390625f};
-  return m[deg];
-}
 
 // `dens` = 1: rows are [density logit, 7 + 3K parameters] and `opac` receives the mapped opacity; 0: rows are the 7 + 3K
 // parameters only (the adapter's own contract).
@@ -39,19 +33,17 @@ adapter_forward_kernel(const float* __restrict__ raw_all, int64_t n, int K, floa
   const float* tile = tile_all + dens;           // row g of the 7 + 3K parameters starts at tile + g * R
   if (dens && opac) {
     for (int g = threadIdx.x; g < rows; g += AD_THREADS) {
-      const float p = 1.0f / (1.0f + expf(-tile_all[g * R]));
-      opac[g0 + g] = 0.5f * ((1.0f - powf(1.0f - p, exponent)) + powf(p, 1.0f / exponent));
+      opac[g0 + g] = head_opacity(tile_all[g * R], exponent);
     }
   }
   for (int i = threadIdx.x; i < rows * 3; i += AD_THREADS) {
     const int g = i / 3, c = i - g * 3;
-    scales[g0 * 3 + i] = fminf(0.001f * softplus_t(tile[g * R + c]), 0.3f);
+    scales[g0 * 3 + i] = head_scale(tile[g * R + c]);
   }
   for (int i = threadIdx.x; i < rows * 4; i += AD_THREADS) {
     const int g = i >> 2, c = i & 3;
     const float* q = tile + g * R + 3;
-    const float nrm = sqrtf((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
-    rots[g0 * 4 + i] = q[c] / (nrm + eps);
+    rots[g0 * 4 + i] = __fdiv_rn(q[c], __fadd_rn(quat_norm(q), eps));
   }
   const int W = 3 * K;
   for (int i = threadIdx.x; i < rows * W; i += AD_THREADS) {
@@ -76,31 +68,23 @@ adapter_backward_kernel(const float* __restrict__ raw, const float* __restrict__
   if (dens) {
     // d opacity / d logit = 0.5 (e (1-p)^(e-1) + (1/e) p^(1/e-1)) p (1-p)
     for (int g = threadIdx.x; g < rows; g += AD_THREADS) {
-      const float p = 1.0f / (1.0f + expf(-tile_all[g * R]));
-      const float ie = 1.0f / exponent;
-      const float dy = 0.5f * (exponent * powf(1.0f - p, exponent - 1.0f) + ie * powf(p, ie - 1.0f));
-      tile_all[g * R] = d_opac ? d_opac[g0 + g] * dy * (p * (1.0f - p)) : 0.0f;
+      tile_all[g * R] = d_opac ? d_opac[g0 + g] * head_opacity_grad(tile_all[g * R], exponent) : 0.0f;
     }
   }
   // quaternion part first (needs all four raw components of a row before any is overwritten): one thread per row
   for (int g = threadIdx.x; g < rows; g += AD_THREADS) {
     float* q = tile + g * R + 3;
-    const float q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-    const float nrm = sqrtf((q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3));
-    const float inv = 1.0f / (nrm + eps);
-    const float dot = (q0 * dq[g * 4] + q1 * dq[g * 4 + 1]) + (q2 * dq[g * 4 + 2] + q3 * dq[g * 4 + 3]);
+    const float qr[4] = {q[0], q[1], q[2], q[3]};
+    float o4[4];
     // d/dq_raw [ q / (|q| + eps) ] = dq/(n+eps) - q (q . dq) / (n (n+eps)^2)
-    const float k = (nrm > 0.0f) ? dot * inv * inv / nrm : 0.0f;
-    q[0] = dq[g * 4] * inv - q0 * k; q[1] = dq[g * 4 + 1] * inv - q1 * k;
-    q[2] = dq[g * 4 + 2] * inv - q2 * k; q[3] = dq[g * 4 + 3] * inv - q3 * k;
+    head_quat_grad(qr, dq + g * 4, eps, o4);
+    q[0] = o4[0]; q[1] = o4[1]; q[2] = o4[2]; q[3] = o4[3];
   }
   for (int i = threadIdx.x; i < rows * 3; i += AD_THREADS) {
     const int g = i / 3, c = i - g * 3;
     const float x = tile[g * R + c];
-    const float sp = 0.001f * softplus_t(x);
-    const float sig = 1.0f / (1.0f + expf(-x));
     const float gs = d_scales ? d_scales[g0 * 3 + i] : 0.0f;
-    tile[g * R + c] = (sp < 0.3f || sp == 0.3f) ? gs * 0.001f * ((x > 20.0f) ? 1.0f : sig) : 0.0f;   // clamp_max passes at equality
+    tile[g * R + c] = gs * head_scale_grad(x);
   }
   const int W = 3 * K;
   for (int i = threadIdx.x; i < rows * W; i += AD_THREADS) {

@@ -76,6 +76,29 @@ int check_desc(const SpfRasterDesc* desc) {
 
 int check_in(const SpfRasterDesc* desc, const SpfRasterIn* in) {
   if (!in) return fail(SPF_ERR_BAD_ARG, "in is NULL");
+  if (in->raw_head) {
+    // raw-head input: the adapter's tensors must not be given as well
+    if (!in->means3D) return fail(SPF_ERR_BAD_ARG, "means3D must be provided");
+    if (in->scales || in->rotations || in->shs || in->colors_precomp)
+      return fail(SPF_ERR_BAD_ARG, "raw_head given: scales / rotations / shs / colors_precomp must be NULL");
+    if ((in->opacities == nullptr) != (in->raw_has_density != 0))
+      return fail(SPF_ERR_BAD_ARG, "raw_head: opacities must be NULL exactly when the rows carry a density logit");
+    const int K = (desc->sh_degree + 1) * (desc->sh_degree + 1);
+    if (in->sh_coeffs < K || in->sh_coeffs > spf::MAX_SH_COEFFS) return fail(SPF_ERR_BAD_ARG, "raw_head: bad sh_coeffs");
+    if (in->raw_stride != (in->raw_has_density ? 1 : 0) + 7 + 3 * in->sh_coeffs)
+      return fail(SPF_ERR_BAD_ARG, "raw_stride must be raw_has_density + 7 + 3 * sh_coeffs");
+    if (!(in->opacity_exponent > 0.0f)) return fail(SPF_ERR_BAD_ARG, "opacity_exponent must be positive");
+    if (desc->n_gaussians % 4 != 0 || (int64_t)desc->n_scenes * desc->views_per_scene > 32)
+      return fail(SPF_ERR_UNSUPPORTED, "raw_head needs n_gaussians % 4 == 0 and at most 32 views per call");
+    if ((reinterpret_cast<uintptr_t>(in->raw_head) | reinterpret_cast<uintptr_t>(in->means3D) |
+         reinterpret_cast<uintptr_t>(in->opacities)) & 15)
+      return fail(SPF_ERR_BAD_ARG, "raw_head / means3D / opacities must be 16-byte aligned");
+    if (desc->flags & (SPF_FLAG_NO_TMA | SPF_FLAG_QUAT_XYZW))
+      return fail(SPF_ERR_UNSUPPORTED, "raw_head does not combine with SPF_FLAG_NO_TMA / SPF_FLAG_QUAT_XYZW");
+    if (!in->viewmatrix || !in->projmatrix || !in->tanfov || !in->bg)
+      return fail(SPF_ERR_BAD_ARG, "viewmatrix / projmatrix / tanfov / bg must be provided");
+    return 0;
+  }
   if (!in->means3D || !in->scales || !in->rotations || !in->opacities)
     return fail(SPF_ERR_BAD_ARG, "means3D / scales / rotations / opacities must be provided");
   if ((in->shs != nullptr) == (in->colors_precomp != nullptr))
@@ -160,12 +183,20 @@ int spf_raster_backward_stages(const SpfRasterDesc* desc, const SpfRasterIn* in,
   int rc;
   if ((rc = check_desc(desc)) || (rc = check_in(desc, in)) || (rc = check_state(st))) return rc;
   if (!gout || !gin) return fail(SPF_ERR_BAD_ARG, "gradient structs must be provided");
-  if (!gin->dup_grad || !gin->pose_partial || !gin->dL_dmeans3D || !gin->dL_dscales || !gin->dL_drotations ||
-      !gin->dL_dopacities || !gin->dL_dviewmatrix)
-    return fail(SPF_ERR_BAD_ARG, "dup_grad, pose_partial and the dL_d{means3D,scales,rotations,opacities,viewmatrix} buffers are required");
-  if (in->shs && !gin->dL_dshs) return fail(SPF_ERR_BAD_ARG, "dL_dshs is required when shs are given");
-  if ((reinterpret_cast<uintptr_t>(gin->dup_grad) & 15) || (reinterpret_cast<uintptr_t>(gin->dL_drotations) & 15))
-    return fail(SPF_ERR_BAD_ARG, "dup_grad / dL_drotations must be 16-byte aligned");
+  if (in->raw_head) {
+    if (!gin->dup_grad || !gin->pose_partial || !gin->dL_dmeans3D || !gin->dL_dviewmatrix || !gin->dL_draw_head)
+      return fail(SPF_ERR_BAD_ARG, "raw_head: dup_grad, pose_partial, dL_dmeans3D, dL_dviewmatrix and dL_draw_head are required");
+    if (!in->raw_has_density && !gin->dL_dopacities) return fail(SPF_ERR_BAD_ARG, "raw_head without density: dL_dopacities is required");
+    if ((reinterpret_cast<uintptr_t>(gin->dup_grad) | reinterpret_cast<uintptr_t>(gin->dL_draw_head)) & 15)
+      return fail(SPF_ERR_BAD_ARG, "dup_grad / dL_draw_head must be 16-byte aligned");
+  } else {
+    if (!gin->dup_grad || !gin->pose_partial || !gin->dL_dmeans3D || !gin->dL_dscales || !gin->dL_drotations ||
+        !gin->dL_dopacities || !gin->dL_dviewmatrix)
+      return fail(SPF_ERR_BAD_ARG, "dup_grad, pose_partial and the dL_d{means3D,scales,rotations,opacities,viewmatrix} buffers are required");
+    if (in->shs && !gin->dL_dshs) return fail(SPF_ERR_BAD_ARG, "dL_dshs is required when shs are given");
+    if ((reinterpret_cast<uintptr_t>(gin->dup_grad) & 15) || (reinterpret_cast<uintptr_t>(gin->dL_drotations) & 15))
+      return fail(SPF_ERR_BAD_ARG, "dup_grad / dL_drotations must be 16-byte aligned");
+  }
   spf::Dims d;
   make_dims(desc, in->sh_coeffs, in->shs != nullptr, d);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -11,6 +11,7 @@
 //
 // Replaces preprocess-backward of diff_gauss_pose incl. the viewmatrix gradient its `pose` branch
 // adds (call site /root/reference/src/model/decoder/cuda_splatting.py:128-138).
+#include "spf_adapter_math.cuh"
 #include "spf_device.cuh"
 #include "spf_kernels.h"
 #include "spf_math.h"
@@ -222,6 +223,194 @@ project_backward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGrad
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Raw-head variant (SpfRasterIn.raw_head): the block's 128 head-output rows [density logit?, 3 scale logits, 4 quaternion
+// components, 3 x K SH coefficients] arrive by one bulk copy; scales / rotations / opacity are re-derived from them in
+// registers (spf_adapter_math.cuh), the SH part is masked in place, and the gradient of the WHOLE row -- SH gradient
+// times the mask, scale gradient through softplus / clamp, quaternion gradient through the normalisation, opacity
+// gradient through the mapping and the sigmoid -- is assembled in shared memory (in place when a scene has one view)
+// and leaves by one bulk store into dL_draw_head.  dL/d{scales, rotations, shs} never exist in HBM.
+template <bool MULTI>
+__global__ void __launch_bounds__(PROJ_THREADS, MULTI ? 2 : 4)
+project_backward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRasterGradIn gin) {
+  pdl_enter();
+  extern __shared__ __align__(128) float smem[];
+  __shared__ ViewConsts vc;
+  __shared__ float pose_warp[PROJ_THREADS / 32][15];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int scene = blockIdx.y;
+  const int g0 = blockIdx.x * PROJ_THREADS;
+  const int g = g0 + tid;
+  const int nvalid = min(PROJ_THREADS, d.P - g0);
+  const int R = in.raw_stride, dens = in.raw_has_density ? 1 : 0, K = in.sh_coeffs;
+  const bool cov_grad = !(d.flags & SPF_FLAG_NO_COV_GRAD);
+  const bool sh_grad = !(d.flags & SPF_FLAG_NO_SH_GRAD);
+  const size_t row_off = ((size_t)scene * d.P + g0) * R;
+  const uint32_t bytes = (uint32_t)nvalid * R * 4u;
+  float* raw_s = smem;                                           // raw rows [128][R]
+  float* out_s = MULTI ? smem + PROJ_THREADS * R : smem;         // gradient rows [128][R] (in place if !MULTI)
+  float* myraw = raw_s + tid * R;
+  float* myout = out_s + tid * R;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bar, bytes);
+    tma_load_1d(raw_s, in.raw_head + row_off, bytes, &bar);
+  }
+  if (MULTI)
+    for (int i = tid; i < PROJ_THREADS * R; i += PROJ_THREADS) out_s[i] = 0.0f;
+
+  const size_t sg = (size_t)scene * d.P + g;
+  float m_in[3] = {0, 0, 0};
+  if (g < d.P)
+    for (int i = 0; i < 3; ++i) m_in[i] = __ldg(in.means3D + sg * 3 + i);
+  float xs[3] = {0, 0, 0}, qraw[4] = {1, 0, 0, 0}, logit = 0.0f;     // this Gaussian's raw parameters
+  float s_in[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
+  bool have_row = false;
+  float dm[3] = {0, 0, 0}, ds[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0}, dop = 0.0f;
+
+  for (int vi = 0; vi < d.v; ++vi) {
+    const int view = scene * d.v + vi;
+    const size_t vg = (size_t)view * d.P + g;
+    int tiles = 0, off = 0;
+    float3 rgbv = make_float3(0.f, 0.f, 0.f);
+    if (g < d.P) {
+      tiles = st.tiles_touched[vg];
+      off = st.dup_offset[vg];
+      rgbv = make_float3(st.rgb[vg * 3], st.rgb[vg * 3 + 1], st.rgb[vg * 3 + 2]);
+    }
+    __syncthreads();   // previous view's vc / pose_warp fully consumed; mbarrier init visible
+    if (tid == 0) {
+      float V[16], Pm[16], bg[3];
+      for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[view * 16 + i]; Pm[i] = in.projmatrix[view * 16 + i]; }
+      for (int i = 0; i < 3; ++i) bg[i] = in.bg[view * 3 + i];
+      make_view_consts(vc, V, Pm, in.tanfov[view * 2], in.tanfov[view * 2 + 1], bg, d.mod, d.W, d.H);
+    }
+    // sum this Gaussian's duplicate records (contiguous slots) while thread 0 builds the view constants
+    float a[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a[k] = 0.0f;
+    if (tiles > 0) {
+      const int ndup = (int)max((int64_t)0, min((int64_t)tiles, d.cap - (int64_t)off));
+      const float4* rec = reinterpret_cast<const float4*>(gin.dup_grad) + 3 * (size_t)off;
+      for (int j = 0; j < ndup; ++j) {
+        const float4 r0 = rec[3 * j], r1 = rec[3 * j + 1];
+        const float2 r2 = *reinterpret_cast<const float2*>(rec + 3 * j + 2);
+        a[0] += r0.x; a[1] += r0.y; a[2] += r0.z; a[3] += r0.w;
+        a[4] += r1.x; a[5] += r1.y; a[6] += r1.z; a[7] += r1.w;
+        a[8] += r2.x; a[9] += r2.y;
+      }
+    }
+    __syncthreads();
+    if (!have_row) {
+      // the raw rows have landed: take this Gaussian's parameters into registers and mask its SH coefficients in place
+      mbar_wait(&bar, 0);
+      if (g < d.P) {
+        if (dens) logit = myraw[0];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { xs[c] = myraw[dens + c]; s_in[c] = head_scale(xs[c]); }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) qraw[c] = myraw[dens + 3 + c];
+        head_quat(qraw, in.raw_eps, q);
+        float* shp = myraw + dens + 7;
+        for (int j = 0; j < 3 * K; ++j) shp[j] = shp[j] * sh_mask_of(j % K);
+      }
+      have_row = true;
+    }
+    const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
+
+    Grad3D o;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o.dm[i] = 0.f; o.ds[i] = 0.f; o.dtau[i] = 0.f; o.dcam[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.dq[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o.dA[i] = 0.f;
+
+    if (tiles > 0) {
+      Grad2D g2;
+      g2.dpx = a[0]; g2.dpy = a[1]; g2.dconx = a[2]; g2.dcony = a[3]; g2.dconz = a[4];
+      g2.dopacity = a[5]; g2.drgb[0] = a[6]; g2.drgb[1] = a[7]; g2.drgb[2] = a[8]; g2.ddepth = a[9];
+      dop += g2.dopacity;
+      if (gin.dL_dmeans2D) {
+        float* o2 = gin.dL_dmeans2D + vg * 3;
+        o2[0] = g2.dpx * 0.5f * vc.Wf; o2[1] = g2.dpy * 0.5f * vc.Hf; o2[2] = 0.0f;
+      }
+      const float m[3] = {m_in[0] * ps, m_in[1] * ps, m_in[2] * ps};
+      const float s[3] = {s_in[0] * ps, s_in[1] * ps, s_in[2] * ps};
+      project_backward_geom(vc, m, s, q, g2, cov_grad, o);
+      {
+        const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
+        const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        const float gm[3] = {(__float_as_uint(rgbv.x) >> 31) ? 0.0f : g2.drgb[0],
+                             (__float_as_uint(rgbv.y) >> 31) ? 0.0f : g2.drgb[1],
+                             (__float_as_uint(rgbv.z) >> 31) ? 0.0f : g2.drgb[2]};
+        float gdir[3];
+        sh_backward_fused<MULTI>(d.deg, dx * inv, dy * inv, dz * inv, myraw + dens + 7, myout + dens + 7, 1, K, gm, gdir[0],
+                                 gdir[1], gdir[2]);
+        if (sh_grad) view_dir_backward(vc, m, gdir, o);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { dm[i] += o.dm[i] * ps; ds[i] += o.ds[i] * ps; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dq[i] += o.dq[i];
+    } else {
+      if (g < d.P && gin.dL_dmeans2D) {
+        float* o2 = gin.dL_dmeans2D + vg * 3;
+        o2[0] = 0.f; o2[1] = 0.f; o2[2] = 0.f;
+      }
+      if (!MULTI && g < d.P) {
+        // in-place mode: a Gaussian that contributes nothing must still hand back a zero SH gradient
+        for (int i = 0; i < 3 * K; ++i) myout[dens + 7 + i] = 0.0f;
+      }
+    }
+
+    // pose contribution: 15 floats, warp shuffle -> block -> partial[view][block]
+    float pv[15];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) pv[i] = o.dA[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { pv[9 + i] = o.dtau[i]; pv[12 + i] = o.dcam[i]; }
+#pragma unroll
+    for (int i = 0; i < 15; ++i) pv[i] = warp_sum(pv[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 15; ++i) pose_warp[wid][i] = pv[i];
+    }
+    __syncthreads();
+    if (tid < 15) {
+      float sum = 0.0f;
+      for (int w = 0; w < PROJ_THREADS / 32; ++w) sum += pose_warp[w][tid];
+      gin.pose_partial[((size_t)view * d.NB + blockIdx.x) * 16 + tid] = sum;
+    }
+  }
+
+  if (g < d.P) {
+    for (int i = 0; i < 3; ++i) gin.dL_dmeans3D[sg * 3 + i] = dm[i];
+    // the rest of the row: SH gradient x mask, scale logits, raw quaternion, density logit
+    float* shg = myout + dens + 7;
+    for (int j = 0; j < 3 * K; ++j) shg[j] = shg[j] * sh_mask_of(j % K);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) myout[dens + c] = ds[c] * head_scale_grad(xs[c]);
+    float o4[4];
+    head_quat_grad(qraw, dq, in.raw_eps, o4);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) myout[dens + 3 + c] = o4[c];
+    if (dens) myout[0] = (dop != 0.0f) ? dop * head_opacity_grad(logit, in.opacity_exponent) : 0.0f;
+    else gin.dL_dopacities[sg] = dop;
+  }
+  fence_proxy_async();     // generic-proxy writes of out_s -> visible to the bulk-copy (async) proxy
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_1d(gin.dL_draw_head + row_off, out_s, bytes);
+    tma_store_commit();
+    tma_store_wait_all();  // shared memory must stay valid until the copy engine has read it
+  }
+}
+
 // K9: dL/dviewmatrix[view] = fixed-order sum of block partials, campos gradient folded in.  One CTA per view:
 // 15 components x 16 interleaved slices on 240 threads (independent, pipelined loads), then a 16-way fixed-order sum.
 __global__ void __launch_bounds__(256)
@@ -276,8 +465,20 @@ static cudaError_t launch_pb(const Dims& d, const SpfRasterIn& in, const SpfRast
   return cudaGetLastError();
 }
 
+template <bool MULTI>
+static cudaError_t launch_pb_raw(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st, const SpfRasterGradIn& gin,
+                                 cudaStream_t s) {
+  const size_t smem = (size_t)(MULTI ? 2 : 1) * PROJ_THREADS * in.raw_stride * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(project_backward_raw_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(d.NB, d.S);
+  pdl_launch(project_backward_raw_kernel<MULTI>, grid, PROJ_THREADS, smem, s)(d, in, st, gin);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_project_backward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                     const SpfRasterGradIn& gin, cudaStream_t s) {
+  if (in.raw_head) return d.v > 1 ? launch_pb_raw<true>(d, in, st, gin, s) : launch_pb_raw<false>(d, in, st, gin, s);
   return d.v > 1 ? launch_pb<true>(d, in, st, gin, s) : launch_pb<false>(d, in, st, gin, s);
 }
 

@@ -8,6 +8,7 @@
 //
 // Replaces the preprocess stage of diff_gauss_pose (call site
 // /root/reference/src/model/decoder/cuda_splatting.py:128-138; algorithm SURVEY.md App. B 1-10).
+#include "spf_adapter_math.cuh"
 #include "spf_device.cuh"
 #include "spf_kernels.h"
 #include "spf_math.h"
@@ -263,6 +264,129 @@ project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Raw-head variant of the streaming kernel (SpfRasterIn.raw_head): an item's 128 head-output rows
+// [density logit?, 3 scale logits, 4 quaternion components, 3 x K SH coefficients] arrive by ONE bulk copy; the
+// adapter's maps (softplus / clamp, quaternion normalisation, SH mask, density sigmoid + opacity mapping --
+// spf_adapter_math.cuh, the same device functions the stand-alone adapter kernel uses) are applied in registers on the
+// way into the projection, so scales / rotations / harmonics / opacities never exist in HBM.  Same role split, same
+// ring, same arithmetic downstream as the streaming kernel above.
+struct __align__(128) PFRawStage {
+  float raw[PROJ_THREADS * 83];      // rows of R <= 83 floats, packed
+  float means[PROJ_THREADS * 3];
+  float opac[PROJ_THREADS];          // only when the rows carry no density logit
+};
+
+struct PFRawSmem {
+  PFRawStage stage[2];
+  ViewConsts vc[VC_MAX];
+  uint64_t full[2];
+  int warp_tot[2][PROJ_THREADS / 32];
+};
+
+__global__ void __launch_bounds__(2 * PROJ_THREADS, 2)
+project_forward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
+                           int* __restrict__ block_sum) {
+  pdl_enter();
+  extern __shared__ __align__(128) unsigned char pf_smem_raw[];
+  PFRawSmem& S = *reinterpret_cast<PFRawSmem*>(pf_smem_raw);
+  const int tid = threadIdx.x;
+  const int R = in.raw_stride, dens = in.raw_has_density ? 1 : 0;
+  const int total = d.B * d.NB;
+
+  if (tid == 0) { mbar_init(&S.full[0], 1); mbar_init(&S.full[1], 1); mbar_fence_init(); }
+  if (tid < d.B) {
+    float V[16], Pm[16], bg[3];
+    for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[tid * 16 + i]; Pm[i] = in.projmatrix[tid * 16 + i]; }
+    for (int i = 0; i < 3; ++i) bg[i] = in.bg[tid * 3 + i];
+    make_view_consts(S.vc[tid], V, Pm, in.tanfov[tid * 2], in.tanfov[tid * 2 + 1], bg, d.mod, d.W, d.H);
+  }
+  __syncthreads();
+
+  auto issue = [&](int item, int sidx) {      // thread 0 only
+    const int view = item / d.NB, chunk = item - view * d.NB;
+    const int scene = view / d.v;
+    const int g0 = chunk * PROJ_THREADS;
+    const uint32_t nv = (uint32_t)min(PROJ_THREADS, d.P - g0);
+    const size_t sg0 = (size_t)scene * d.P + g0;
+    PFRawStage& T = S.stage[sidx];
+    mbar_expect_tx(&S.full[sidx], nv * (uint32_t)(R * 4 + 12 + (dens ? 0 : 4)));
+    tma_load_1d(T.raw, in.raw_head + sg0 * R, nv * (uint32_t)R * 4u, &S.full[sidx]);
+    tma_load_1d(T.means, in.means3D + sg0 * 3, nv * 12u, &S.full[sidx]);
+    if (!dens) tma_load_1d(T.opac, in.opacities + sg0, nv * 4u, &S.full[sidx]);
+  };
+
+  int item = blockIdx.x;
+  if (tid == 0 && item < total) issue(item, 0);
+  for (int k = 0; item < total; ++k, item += gridDim.x) {
+    const int sidx = k & 1;
+    if (tid == 0 && item + (int)gridDim.x < total) issue(item + gridDim.x, sidx ^ 1);
+    const int view = item / d.NB, chunk = item - view * d.NB;
+    const int role = tid >> 7, gi = tid & (PROJ_THREADS - 1);   // warps 0-3: geometry, warps 4-7: SH colour
+    const int g = chunk * PROJ_THREADS + gi;
+    const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
+    const ViewConsts& vc = S.vc[view];
+    const PFRawStage& T = S.stage[sidx];
+    mbar_wait(&S.full[sidx], (uint32_t)((k >> 1) & 1));
+    const float* rowp = T.raw + gi * R + dens;                  // [3 scale logits, 4 quaternion, 3 x K SH]
+
+    int tiles = 0, cx0 = 0, cy0 = 0, cw = 1;
+    const size_t vg = (size_t)view * d.P + g;
+    if (role == 1) {
+      if (g < d.P) {
+        float m[3];
+        for (int i = 0; i < 3; ++i) m[i] = T.means[gi * 3 + i] * ps;
+        const float dx = m[0] - vc.campos[0], dy = m[1] - vc.campos[1], dz = m[2] - vc.campos[2];
+        const float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
+        float pre[3];
+        sh_eval_fused_t<true>(d.deg, dx * inv, dy * inv, dz * inv, rowp + 7, 1, in.sh_coeffs, pre);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float p5 = pre[c] + 0.5f;
+          st.rgb[vg * 3 + c] = (p5 < 0.0f) ? -0.0f : p5;     // sign bit = clamp mask for the backward
+        }
+      }
+    } else if (g < d.P) {
+      float m[3], s[3], q[4];
+      for (int i = 0; i < 3; ++i) { m[i] = T.means[gi * 3 + i] * ps; s[i] = head_scale(rowp[i]) * ps; }
+      {
+        const float qr[4] = {rowp[3], rowp[4], rowp[5], rowp[6]};
+        head_quat(qr, in.raw_eps, q);
+      }
+      const float opac = dens ? head_opacity(T.raw[gi * R], in.opacity_exponent) : T.opac[gi];
+      Projected o;
+      const bool vis = project_forward(vc, m, s, q, o);
+      tiles = o.tiles;
+      reinterpret_cast<float2*>(st.xy)[vg] = make_float2(o.px, o.py);
+      st.depth[vg] = o.depth;
+      reinterpret_cast<float4*>(st.conic_opacity)[vg] = make_float4(o.conx, o.cony, o.conz, opac);
+      st.radii[vg] = o.radius;
+      st.tiles_touched[vg] = o.tiles;
+      if (vis) { cx0 = o.rx0; cy0 = o.ry0; cw = o.rx1 - o.rx0; }
+    }
+    if (role == 0) {
+      int* tc = tile_count + (size_t)view * d.T;
+      int maxc = tiles;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+      int x = 0, y = 0;
+      for (int kk = 0; kk < maxc; ++kk) {
+        const bool has = kk < tiles;
+        warp_aggregated_add(has, tc, (cy0 + y) * d.gx + cx0 + x, tid & 31);
+        if (++x == cw) { x = 0; ++y; }
+      }
+    }
+    const int wsum = warp_sum_i(tiles);
+    if (role == 0 && (tid & 31) == 0) S.warp_tot[sidx][tid >> 5] = wsum;
+    __syncthreads();     // stage sidx fully consumed (it is refilled two items later); warp totals visible
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < PROJ_THREADS / 32; ++w) t += S.warp_tot[sidx][w];
+      block_sum[(size_t)view * d.NB + chunk] = t;
+    }
+  }
+}
+
 static bool stream_ok(const Dims& d, const SpfRasterIn& in) {
   if (!in.shs) return false;
   const int row = 3 * in.sh_coeffs;
@@ -276,6 +400,15 @@ static bool stream_ok(const Dims& d, const SpfRasterIn& in) {
 
 cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                    const ControlLayout& cl, cudaStream_t s) {
+  if (in.raw_head) {      // (shape / alignment requirements were checked by the C entry point)
+    cudaError_t e = cudaFuncSetAttribute(project_forward_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PFRawSmem));
+    if (e != cudaSuccess) return e;
+    const int grid1 = min(d.B * d.NB, 2 * sm_count());
+    pdl_launch(project_forward_raw_kernel, grid1, 2 * PROJ_THREADS, sizeof(PFRawSmem), s)(d, in, st, st.control + cl.tile_count,
+                                                                                  st.control + cl.block_sum);
+    return cudaGetLastError();
+  }
   const int row = 3 * in.sh_coeffs;
   const int stride = (row & 1) ? row : row + 1;
   const size_t smem = in.shs ? (size_t)PROJ_THREADS * stride * sizeof(float) : 0;

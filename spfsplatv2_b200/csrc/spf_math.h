@@ -246,28 +246,43 @@ SPF_HD void sh_basis_backward(int deg, float x, float y, float z, const float* v
 
 // SH colour of one Gaussian without a basis array: rgb[c] = sum_k B_k(x,y,z) * sh[k*sk + c*sc]  (explicit fmaf so the
 // colour path keeps fused multiply-adds even in the -fmad=false translation unit; not index-affecting).
-SPF_HD void sh_eval_fused(int deg, float x, float y, float z, const float* sh, int sk, int sc, float rgb[3]) {
+// MASKED: every coefficient is first multiplied by the encoder's per-degree SH mask (1 for degree 0, 0.1 * 0.25^d above,
+// gaussian_adapter.py:42-48) -- the raw-head input path, where the masked coefficients never exist in memory; the
+// product is rounded to fp32 before the fma, exactly like the stand-alone adapter stores it.
+constexpr float SH_MASK_1 = 0.1f * 0.25f, SH_MASK_2 = 0.1f * 0.0625f, SH_MASK_3 = 0.1f * 0.015625f,
+                SH_MASK_4 = 0.1f * 0.00390625f;
+
+template <bool MASKED>
+SPF_HD void sh_eval_fused_t(int deg, float x, float y, float z, const float* sh, int sk, int sc, float rgb[3]) {
   float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+  float mk = 1.0f;
 #define SPF_SH_EVAL(k, B)                                                                  \
   {                                                                                        \
     const float b_ = (B);                                                                  \
     const int i_ = (k) * sk;                                                               \
-    r0 = fmaf(b_, sh[i_], r0); r1 = fmaf(b_, sh[i_ + sc], r1); r2 = fmaf(b_, sh[i_ + 2 * sc], r2); \
+    const float s0_ = MASKED ? sh[i_] * mk : sh[i_];                                       \
+    const float s1_ = MASKED ? sh[i_ + sc] * mk : sh[i_ + sc];                             \
+    const float s2_ = MASKED ? sh[i_ + 2 * sc] * mk : sh[i_ + 2 * sc];                     \
+    r0 = fmaf(b_, s0_, r0); r1 = fmaf(b_, s1_, r1); r2 = fmaf(b_, s2_, r2);                \
   }
   SPF_SH_EVAL(0, SH_C0)
   if (deg >= 1) {
+    mk = SH_MASK_1;
     SPF_SH_EVAL(1, -SH_C1 * y) SPF_SH_EVAL(2, SH_C1 * z) SPF_SH_EVAL(3, -SH_C1 * x)
     if (deg >= 2) {
+      mk = SH_MASK_2;
       const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
       SPF_SH_EVAL(4, SH_C2_0 * xy) SPF_SH_EVAL(5, SH_C2_1 * yz) SPF_SH_EVAL(6, SH_C2_2 * (2.0f * zz - xx - yy))
       SPF_SH_EVAL(7, SH_C2_3 * xz) SPF_SH_EVAL(8, SH_C2_4 * (xx - yy))
       if (deg >= 3) {
+        mk = SH_MASK_3;
         SPF_SH_EVAL(9, SH_C3_0 * y * (3.0f * xx - yy)) SPF_SH_EVAL(10, SH_C3_1 * xy * z)
         SPF_SH_EVAL(11, SH_C3_2 * y * (4.0f * zz - xx - yy))
         SPF_SH_EVAL(12, SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy))
         SPF_SH_EVAL(13, SH_C3_4 * x * (4.0f * zz - xx - yy)) SPF_SH_EVAL(14, SH_C3_5 * z * (xx - yy))
         SPF_SH_EVAL(15, SH_C3_6 * x * (xx - 3.0f * yy))
         if (deg >= 4) {
+          mk = SH_MASK_4;
           SPF_SH_EVAL(16, SH_C4_0 * xy * (xx - yy)) SPF_SH_EVAL(17, SH_C4_1 * yz * (3.0f * xx - yy))
           SPF_SH_EVAL(18, SH_C4_2 * xy * (7.0f * zz - 1.0f)) SPF_SH_EVAL(19, SH_C4_3 * yz * (7.0f * zz - 3.0f))
           SPF_SH_EVAL(20, SH_C4_4 * (zz * (35.0f * zz - 30.0f) + 3.0f)) SPF_SH_EVAL(21, SH_C4_5 * xz * (7.0f * zz - 3.0f))
@@ -279,6 +294,11 @@ SPF_HD void sh_eval_fused(int deg, float x, float y, float z, const float* sh, i
   }
 #undef SPF_SH_EVAL
   rgb[0] = r0; rgb[1] = r1; rgb[2] = r2;
+  (void)mk;
+}
+
+SPF_HD void sh_eval_fused(int deg, float x, float y, float z, const float* sh, int sk, int sc, float rgb[3]) {
+  sh_eval_fused_t<false>(deg, x, y, z, sh, sk, sc, rgb);
 }
 
 // Fused single pass over the SH coefficients for the backward (no Bk[] / vk[] arrays => few live registers):

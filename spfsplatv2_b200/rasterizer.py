@@ -305,7 +305,10 @@ def _launch_forward(st: "_State", fixed: _Workspace, cap: int, color, depth, alp
 
 
 def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg,
-                  pre_scale, pair_log: bool = False, defer_count: bool = False):
+                  pre_scale, pair_log: bool = False, defer_count: bool = False, raw=None):
+    """``raw`` = (head rows [S,P,R], has_density, eps, opacity_exponent) selects the raw-head input of the projection
+    kernels (SpfRasterIn.raw_head); scales / rots / shs / colors are then None (and opac too when the rows carry the
+    density logit)."""
     lib = L.lib()
     dev = means.device
     if dev.type != "cuda":
@@ -318,10 +321,16 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
         raise ValueError(f"viewmatrix has {viewmat.shape[0]} views, expected n_scenes*views_per_scene={B}")
     T = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
     use_sh = shs is not None
-    if use_sh == (colors is not None):
-        raise Exception("Please provide excatly one of either SHs or precomputed colors!")
     K = 0
-    if use_sh:
+    if raw is not None:
+        raw_head, has_density, raw_eps, exponent = raw
+        R = raw_head.shape[-1]
+        K = (R - (1 if has_density else 0) - 7) // 3
+        if raw_head.shape[:2] != (S, P) or R != (1 if has_density else 0) + 7 + 3 * K or K < (s.sh_degree + 1) ** 2:
+            raise ValueError(f"head rows {tuple(raw_head.shape)} do not match means {tuple(means.shape)} / sh_degree {s.sh_degree}")
+    elif use_sh == (colors is not None):
+        raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+    elif use_sh:
         K = shs.shape[-1] if s.sh_layout_ck else shs.shape[-2]
 
     f32, i32 = torch.float32, torch.int32
@@ -355,6 +364,11 @@ def _forward_impl(s: RasterSettings, means, scales, rots, opac, shs, colors, vie
     st.cin = L.SpfRasterIn(_ptr(means), _ptr(scales), _ptr(rots), _ptr(opac), _ptr(shs), _ptr(colors), K,
                            _ptr(viewmat), _ptr(projmat), _ptr(tanfov), _ptr(bg), _ptr(pre_scale))
     st.keep = (means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale)
+    if raw is not None:
+        st.cin.raw_head = _ptr(raw_head)
+        st.cin.raw_stride, st.cin.raw_has_density = R, int(bool(has_density))
+        st.cin.raw_eps, st.cin.opacity_exponent = float(raw_eps), float(exponent)
+        st.keep = st.keep + (raw_head,)
     spec = [("xy", (B, P, 2), f32), ("depth", (B, P), f32), ("conic_opacity", (B, P, 4), f32), ("rgb", (B, P, 3), f32),
             ("radii", (B, P), i32), ("tiles_touched", (B, P), i32), ("dup_offset", (B, P), i32), ("control", (n_ctrl,), i32),
             ("tile_ranges", (B * T, 2), i32), ("final_T", (B, H, W), f32), ("n_contrib", (B, H, W), i32),
@@ -416,57 +430,87 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, g_depth, g_alpha, _g_radii):
-        s: RasterSettings = ctx.settings
-        st: _State = ctx.st
-        lib = L.lib()
-        means, scales, rots, opac, shs, colors, viewmat, projmat, tanfov, bg, pre_scale = st.keep
-        dev = means.device
-        S, P = means.shape[0], means.shape[1]
-        B = S * s.views_per_scene
-        NB = (P + PROJ_THREADS - 1) // PROJ_THREADS
-        f32 = dict(dtype=torch.float32, device=dev)
-        # deferred duplicate-count check (the forward did not wait for it; by now the count has long landed)
-        n = st.n_dups
-        pend = _unverified.get(st.key)
-        if pend is not None and pend[2] == st.ticket:
-            _unverified.pop(st.key, None)
-        if not st.captured:
-            with _lock:
-                _capacity_hint[st.key] = max(int(_capacity_hint.get(st.key, 0)), int(n * GROWTH) + 1024)
-            if n > st.capacity:
-                raise DuplicateCapacityError(
-                    f"spfsplatv2_b200: {n} tile duplicates exceeded the buffer capacity {st.capacity} chosen from earlier "
-                    "calls of this shape; the forward image of this step was NaN-poisoned (so was any loss computed from "
-                    "it).  The capacity has been raised: run the step again.")
-        gc = None if g_color is None else _f32c(g_color)
-        gd = None if g_depth is None else _f32c(g_depth)
-        ga = None if (g_alpha is None or not s.want_alpha) else _f32c(g_alpha)
-        gout = L.SpfRasterGradOut(_ptr(gc), _ptr(gd), _ptr(ga))
-        scratch = _Workspace(dev, [("dup_grad", (max(n, 1), 12), torch.float32), ("pose_partial", (B, NB, 16), torch.float32)])
-        d_means = torch.empty_like(means)
-        d_scales = torch.empty_like(scales)
-        d_rots = torch.empty_like(rots)
-        d_opac = torch.empty_like(opac)
-        d_shs = torch.empty_like(shs) if shs is not None else None
-        d_cols = torch.empty_like(colors) if colors is not None else None
-        d_view = torch.empty(B, 16, **f32)
-        d_m2d = torch.empty(B, P, 3, **f32) if (s.want_means2d_grad and ctx.shapes[7] is not None) else None
-        gin = L.SpfRasterGradIn(scratch.ptr("dup_grad"), scratch.ptr("pose_partial"), _ptr(d_means), _ptr(d_scales),
-                                _ptr(d_rots), _ptr(d_opac), _ptr(d_shs), _ptr(d_cols), _ptr(d_view), _ptr(d_m2d))
-        with torch.cuda.device(dev):
-            L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
-                                            C.byref(gin), _stream(dev)), "spf_raster_backward")
-        if st.desc.pair_capacity > 0 and not st.captured and len(_pair_stat.setdefault(st.key, [])) < 4:
-            # feed the largest per-warp pair count back to the sizing of the next forward (no wait)
-            pin, ev = _pin_pool.pop() if _pin_pool else (torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
-            pin.copy_(st.tensors["control"][2:3], non_blocking=True)
-            ev.record(torch.cuda.current_stream(dev))
-            _pair_stat[st.key].append([pin, ev, 0])
         sh = ctx.shapes
-        return (None, d_means.view(sh[0]), d_scales.view(sh[1]), d_rots.view(sh[2]), d_opac.view(sh[3]),
-                None if d_shs is None else d_shs.view(sh[4]), None if d_cols is None else d_cols.view(sh[5]),
-                d_view.view(sh[6]), None, None, None, None,
-                None if d_m2d is None else d_m2d.view(sh[7]))
+        g = _backward_impl(ctx.st, ctx.settings, g_color, g_depth, g_alpha, want_m2d=sh[7] is not None)
+        v = lambda t, shape: None if t is None else t.view(shape)
+        return (None, v(g["means"], sh[0]), v(g["scales"], sh[1]), v(g["rots"], sh[2]), v(g["opac"], sh[3]),
+                v(g["shs"], sh[4]), v(g["cols"], sh[5]), v(g["view"], sh[6]), None, None, None, None, v(g["m2d"], sh[7]))
+
+
+def _backward_impl(st: "_State", s: RasterSettings, g_color, g_depth, g_alpha, want_m2d: bool) -> dict:
+    """Deferred duplicate-count check, gradient buffers, spf_raster_backward, pair-log sizing feedback.  Returns the
+    gradient tensors by name (``raw`` instead of scales / rots / shs for a raw-head forward)."""
+    lib = L.lib()
+    means, scales, rots, opac, shs, colors = st.keep[:6]
+    raw_head = st.keep[11] if len(st.keep) > 11 else None
+    dev = means.device
+    S, P = means.shape[0], means.shape[1]
+    B = S * s.views_per_scene
+    NB = (P + PROJ_THREADS - 1) // PROJ_THREADS
+    f32 = dict(dtype=torch.float32, device=dev)
+    # deferred duplicate-count check (the forward did not wait for it; by now the count has long landed)
+    n = st.n_dups
+    pend = _unverified.get(st.key)
+    if pend is not None and pend[2] == st.ticket:
+        _unverified.pop(st.key, None)
+    if not st.captured:
+        with _lock:
+            _capacity_hint[st.key] = max(int(_capacity_hint.get(st.key, 0)), int(n * GROWTH) + 1024)
+        if n > st.capacity:
+            raise DuplicateCapacityError(
+                f"spfsplatv2_b200: {n} tile duplicates exceeded the buffer capacity {st.capacity} chosen from earlier "
+                "calls of this shape; the forward image of this step was NaN-poisoned (so was any loss computed from "
+                "it).  The capacity has been raised: run the step again.")
+    gc = None if g_color is None else _f32c(g_color)
+    gd = None if g_depth is None else _f32c(g_depth)
+    ga = None if (g_alpha is None or not s.want_alpha) else _f32c(g_alpha)
+    gout = L.SpfRasterGradOut(_ptr(gc), _ptr(gd), _ptr(ga))
+    scratch = _Workspace(dev, [("dup_grad", (max(n, 1), 12), torch.float32), ("pose_partial", (B, NB, 16), torch.float32)])
+    e = lambda t: None if t is None else torch.empty_like(t)
+    g = dict(means=e(means), scales=e(scales), rots=e(rots), opac=e(opac), shs=e(shs), cols=e(colors), raw=e(raw_head),
+             view=torch.empty(B, 16, **f32), m2d=torch.empty(B, P, 3, **f32) if (s.want_means2d_grad and want_m2d) else None)
+    gin = L.SpfRasterGradIn(scratch.ptr("dup_grad"), scratch.ptr("pose_partial"), _ptr(g["means"]), _ptr(g["scales"]),
+                            _ptr(g["rots"]), _ptr(g["opac"]), _ptr(g["shs"]), _ptr(g["cols"]), _ptr(g["view"]), _ptr(g["m2d"]),
+                            _ptr(g["raw"]))
+    with torch.cuda.device(dev):
+        L.check(lib.spf_raster_backward(C.byref(st.desc), C.byref(st.cin), C.byref(st.cstate), C.byref(gout),
+                                        C.byref(gin), _stream(dev)), "spf_raster_backward")
+    if st.desc.pair_capacity > 0 and not st.captured and len(_pair_stat.setdefault(st.key, [])) < 4:
+        # feed the largest per-warp pair count back to the sizing of the next forward (no wait)
+        pin, ev = _pin_pool.pop() if _pin_pool else (torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        pin.copy_(st.tensors["control"][2:3], non_blocking=True)
+        ev.record(torch.cuda.current_stream(dev))
+        _pair_stat[st.key].append([pin, ev, 0])
+    return g
+
+
+class _RasterizeHead(torch.autograd.Function):
+    """Raw-head input: the encoder head's rows go straight into the projection kernels."""
+
+    @staticmethod
+    def forward(ctx, settings: RasterSettings, means, head, opac, viewmat, projmat, tanfov, bg, pre_scale, means2d,
+                eps: float, exponent: float):
+        a = [None if t is None else _f32c(t.detach()) for t in (means, opac, viewmat, projmat, tanfov, bg, pre_scale, head)]
+        need_grad = any(ctx.needs_input_grad)
+        color, depth, alpha, radii, st = _forward_impl(settings, a[0], None, None, a[1], None, None, a[2], a[3], a[4], a[5],
+                                                       a[6], pair_log=need_grad, defer_count=need_grad,
+                                                       raw=(a[7], opac is None, eps, exponent))
+        ctx.settings, ctx.st = settings, st
+        ctx.shapes = (means.shape, head.shape, None if opac is None else opac.shape, viewmat.shape,
+                      None if means2d is None else means2d.shape)
+        ctx.mark_non_differentiable(radii)
+        if alpha is None:
+            alpha = torch.empty(0, device=color.device)
+            ctx.mark_non_differentiable(alpha)
+        return color, depth, alpha, radii
+
+    @staticmethod
+    def backward(ctx, g_color, g_depth, g_alpha, _g_radii):
+        sh = ctx.shapes
+        g = _backward_impl(ctx.st, ctx.settings, g_color, g_depth, g_alpha, want_m2d=sh[4] is not None)
+        v = lambda t, shape: None if t is None else t.view(shape)
+        return (None, v(g["means"], sh[0]), v(g["raw"], sh[1]), v(g["opac"], sh[2]), v(g["view"], sh[3]), None, None, None,
+                None, v(g["m2d"], sh[4]), None, None)
 
 
 _last_state = [None]
@@ -498,6 +542,20 @@ def rasterize_batched(settings: RasterSettings, means: Tensor, scales: Tensor, r
     opacities, shs/colors and viewmatrix."""
     return _Rasterize.apply(settings, means, scales, rotations, opacities, shs, colors, viewmatrix, projmatrix,
                             tanfov, bg, pre_scale, means2d)
+
+
+def rasterize_batched_head(settings: RasterSettings, means: Tensor, head_out: Tensor, viewmatrix: Tensor,
+                           projmatrix: Tensor, tanfov: Tensor, bg: Tensor, pre_scale: Optional[Tensor] = None,
+                           means2d: Optional[Tensor] = None, *, opacities: Optional[Tensor] = None, eps: float = 1e-8,
+                           opacity_exponent: float = 1.0):
+    """Renders straight from the encoder head's rows: ``head_out`` [S,P,1+7+3K] = [density logit, 3 scale logits,
+    4 quaternion components, 3 x K SH coefficients] (or [S,P,7+3K] with ``opacities`` [S,P] given separately, the
+    adapter's own contract).  The adapter's maps and the opacity mapping (gaussian_adapter.py:122-150,
+    encoder_spfsplatv2.py:146-159,255-268) run inside the projection kernels; scales / rotations / harmonics / opacities
+    and their gradients never exist in HBM.  Same outputs as ``rasterize_batched``; differentiable wrt means, head_out,
+    opacities and viewmatrix.  Needs P % 4 == 0 and at most 32 views per call."""
+    return _RasterizeHead.apply(settings, means, head_out, opacities, viewmatrix, projmatrix, tanfov, bg, pre_scale,
+                                means2d, float(eps), float(opacity_exponent))
 
 
 def forward_with_state(settings: RasterSettings, means, scales, rotations, opacities, shs, colors, viewmatrix,
