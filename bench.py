@@ -330,6 +330,11 @@ def run_ours(args):
                 ev.record(cur)
             _prefetch(k % 2)
             e2e_state["primed"] = True
+        # Next step's host->device copy is queued FIRST (its buffer set was released by step k-1), so the copy engine
+        # runs back to back: the host blocks inside this step's backward until the forward's duplicate count has
+        # landed (rasterizer._wait_count), i.e. until copy k has finished, and a copy queued only after that would
+        # start ~0.5 ms late every step.
+        _prefetch((k + 1) % 2)
         cur.wait_event(copied[k % 2])
         d = dict(e2e_bufs[k % 2])
         d["cov"], d["shape"] = dev_in["cov"], (h, w)
@@ -337,7 +342,6 @@ def run_ours(args):
         loss, leaves, ext = _step(dec, Gaussians, d)
         done[k % 2].record(cur)
         ar_launch()
-        _prefetch((k + 1) % 2)                    # next step's host->device copy overlaps this step's kernels
         e2e_state["k"] = k + 1
         return float(loss.item())                 # device->host read of the step's result
 
