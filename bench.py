@@ -500,6 +500,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_rope:
             line["roofline_rope"] = rope_bench(dev, peaks["hbm_gbs"])
+        if world == 1 and not args.no_head:
+            line["head_path"] = head_path_bench(dec, dev_in, h, w, iters=max(10, args.steps))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, sample_views=args.cpu_views)
         print(json.dumps(line), flush=True)
@@ -561,6 +563,82 @@ def rope_bench(dev, hbm_gbs: float, iters: int = 20) -> dict:
                                         "achieved": round(gbs, 1), "frac": round(gbs / hbm_gbs, 4), "bytes": algo, "buffers_cycled": nbuf}
             del bufs, views, graph
     return {"bound": "hbm", "unit": "GB/s", "peak": hbm_gbs, "kernel": "rope2d_kernel (q and k in one launch)", "cases": out}
+
+
+def head_path_bench(dec, dev_in, h, w, iters: int = 20) -> dict:
+    """SURVEY.md 8f rank 2, measured: one training step that STARTS at the encoder head's rows [b, P, 83] (density logit,
+    scale logits, quaternion, SH) -- post-processing (encoder_spfsplatv2.py:255-268, gaussian_adapter.py:122-150) ->
+    decoder -> fused MSE -> backward down to d(head rows) -- (a) unfused: the stand-alone head kernel, then the decoder on
+    its outputs; (b) fused: the rows go straight into the projection kernels (SpfRasterIn.raw_head).  Same scenes as the
+    headline workload (the rows are the inverse images of its scales / rotations / harmonics / opacities).  Each variant
+    is one CUDA graph per step, device-timed."""
+    from spfsplatv2_b200.adapter import GaussianAdapterCfg, UnifiedGaussianAdapter
+    from spfsplatv2_b200.loss import mse_loss
+    dev = dev_in["means"].device
+    ad = UnifiedGaussianAdapter(GaussianAdapterCfg(0.5, 15.0, 4))
+    K = dev_in["harmonics"].shape[-1]
+    mask = torch.ones(K, device=dev)
+    for d in range(1, 5):
+        mask[d * d:(d + 1) ** 2] = 0.1 * 0.25 ** d
+    sc = dev_in["scales"].double() / 0.001
+    head = torch.cat([torch.logit(dev_in["opacities"].double().clamp(1e-6, 1 - 1e-6))[..., None],
+                      torch.where(sc > 20, sc, torch.log(torch.expm1(sc))),
+                      dev_in["rotations"].double(), (dev_in["harmonics"].double() / mask).flatten(-2)], dim=-1).float().contiguous()
+    b = head.shape[0]
+
+    def unfused():
+        hd = head.detach().requires_grad_()
+        m = dev_in["means"].detach().requires_grad_()
+        ext = dev_in["extrinsics"].detach().requires_grad_()
+        out = dec(ad.forward_head(m, hd), ext, dev_in["intrinsics"], dev_in["near"], dev_in["far"], (h, w))
+        loss = mse_loss(out.color, dev_in["gt"])
+        loss.backward()
+        return loss, hd
+
+    def fused():
+        hd = head.detach().requires_grad_()
+        m = dev_in["means"].detach().requires_grad_()
+        ext = dev_in["extrinsics"].detach().requires_grad_()
+        out = dec.forward_head(m, hd, ext, dev_in["intrinsics"], dev_in["near"], dev_in["far"], (h, w), sh_degree=4)
+        loss = mse_loss(out.color, dev_in["gt"])
+        loss.backward()
+        return loss, hd
+
+    res = {}
+    keep = {}
+    for name, fn in (("unfused", unfused), ("fused", fused)):
+        for _ in range(4):
+            loss, hd = fn()
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss, hd = fn()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = {"ms_per_step": round(ms, 4), "views_per_s": round(b / (ms * 1e-3), 1), "loss": float(loss)}
+        keep[name] = (graph, hd.grad.clone())
+    # per-kernel device times of the fused variant
+    from spfsplatv2_b200.camera import camera_setup
+    from spfsplatv2_b200.rasterizer import RasterSettings, profile_stages
+    view, proj, tanfov, scale = camera_setup(dev_in["extrinsics"].reshape(b, 4, 4), dev_in["intrinsics"].reshape(b, 3, 3),
+                                             dev_in["near"].reshape(-1), dev_in["far"].reshape(-1), True)
+    gcol = torch.randn(b, 3, h, w, device=dev) / (b * 3 * h * w)
+    stg = profile_stages(RasterSettings(h, w, 4), dev_in["means"], None, None, None, None, None, view, proj, tanfov,
+                         torch.zeros(b, 3, device=dev), scale, gcol, None, iters=iters, raw=(head, True, 1e-8, 1.0))
+    res["fused"]["stage_ms"] = {k: round(v, 4) for k, v in stg.items() if not k.startswith("_")}
+    gu, gf = keep["unfused"][1].double(), keep["fused"][1].double()
+    res["head_grad_rel_diff"] = float((gf - gu).norm() / (gu.norm() + 1e-30))
+    res["note"] = ("head rows [b,P,83] -> image -> MSE -> d(head rows); unfused = spf_head_forward/backward + decoder, fused = "
+                   "DecoderSplattingCUDA.forward_head (adapter + opacity mapping inside the projection kernels)")
+    return res
 
 
 def cpu_baseline(workload: str, sample_views: int = 3) -> dict:
@@ -691,6 +769,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager PyTorch loop instead of a captured CUDA graph")
     ap.add_argument("--no-rope", action="store_true", help="skip the RoPE roofline block of the N=1 line")
+    ap.add_argument("--no-head", action="store_true", help="skip the head-rows-to-image (fused adapter) block of the N=1 line")
     ap.add_argument("--cpu-views", type=int, default=4)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -306,7 +306,8 @@ project_backward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRaster
     }
     __syncthreads();
     if (!have_row) {
-      // the raw rows have landed: take this Gaussian's parameters into registers and mask its SH coefficients in place
+      // the raw rows have landed: take this Gaussian's parameters into registers (the SH coefficients stay unmasked in
+      // shared memory; sh_backward_fused<., MASKED> applies the mask as it reads them)
       mbar_wait(&bar, 0);
       if (g < d.P) {
         if (dens) logit = myraw[0];
@@ -315,8 +316,6 @@ project_backward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRaster
 #pragma unroll
         for (int c = 0; c < 4; ++c) qraw[c] = myraw[dens + 3 + c];
         head_quat(qraw, in.raw_eps, q);
-        float* shp = myraw + dens + 7;
-        for (int j = 0; j < 3 * K; ++j) shp[j] = shp[j] * sh_mask_of(j % K);
       }
       have_row = true;
     }
@@ -349,8 +348,8 @@ project_backward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRaster
                              (__float_as_uint(rgbv.y) >> 31) ? 0.0f : g2.drgb[1],
                              (__float_as_uint(rgbv.z) >> 31) ? 0.0f : g2.drgb[2]};
         float gdir[3];
-        sh_backward_fused<MULTI>(d.deg, dx * inv, dy * inv, dz * inv, myraw + dens + 7, myout + dens + 7, 1, K, gm, gdir[0],
-                                 gdir[1], gdir[2]);
+        sh_backward_fused<MULTI, true>(d.deg, dx * inv, dy * inv, dz * inv, myraw + dens + 7, myout + dens + 7, 1, K, gm,
+                                       gdir[0], gdir[1], gdir[2]);
         if (sh_grad) view_dir_backward(vc, m, gdir, o);
       }
 #pragma unroll
@@ -390,9 +389,9 @@ project_backward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, SpfRaster
 
   if (g < d.P) {
     for (int i = 0; i < 3; ++i) gin.dL_dmeans3D[sg * 3 + i] = dm[i];
-    // the rest of the row: SH gradient x mask, scale logits, raw quaternion, density logit
-    float* shg = myout + dens + 7;
-    for (int j = 0; j < 3 * K; ++j) shg[j] = shg[j] * sh_mask_of(j % K);
+    // the rest of the row: SH gradient x mask (already applied when a scene has one view), scale logits, raw quaternion,
+    // density logit
+    if (MULTI) sh_mask_rows(myout + dens + 7, K);
 #pragma unroll
     for (int c = 0; c < 3; ++c) myout[dens + c] = ds[c] * head_scale_grad(xs[c]);
     float o4[4];

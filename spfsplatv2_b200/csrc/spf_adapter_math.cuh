@@ -45,16 +45,31 @@ __device__ __forceinline__ void head_quat_grad(const float q[4], const float dq[
   for (int c = 0; c < 4; ++c) out[c] = dq[c] * inv - q[c] * k;
 }
 
+// (exponent 1 -- the shipped schedule, opacity_mapping 0 / 0 -- skips the two powf: x^1 = x)
 __device__ __forceinline__ float head_opacity(float logit, float exponent) {
   const float p = 1.0f / (1.0f + expf(-logit));
+  if (exponent == 1.0f) return 0.5f * ((1.0f - (1.0f - p)) + p);
   return 0.5f * ((1.0f - powf(1.0f - p, exponent)) + powf(p, 1.0f / exponent));
 }
 // d opacity / d logit = 0.5 (e (1-p)^(e-1) + (1/e) p^(1/e-1)) p (1-p)
 __device__ __forceinline__ float head_opacity_grad(float logit, float exponent) {
   const float p = 1.0f / (1.0f + expf(-logit));
+  if (exponent == 1.0f) return p * (1.0f - p);
   const float ie = 1.0f / exponent;
   const float dy = 0.5f * (exponent * powf(1.0f - p, exponent - 1.0f) + ie * powf(p, ie - 1.0f));
   return dy * (p * (1.0f - p));
+}
+
+// v[c * K + k] *= mask(degree of k) for a [3][K] block of one Gaussian (no per-element index arithmetic)
+__device__ __forceinline__ void sh_mask_rows(float* v, int K) {
+  const float m[5] = {1.0f, 0.1f * 0.25f, 0.1f * 0.0625f, 0.1f * 0.015625f, 0.1f * 0.00390625f};
+#pragma unroll
+  for (int dgr = 1; dgr < 5; ++dgr) {
+    const int k1 = min((dgr + 1) * (dgr + 1), K);
+    for (int k = dgr * dgr; k < k1; ++k) {
+      v[k] = __fmul_rn(v[k], m[dgr]); v[K + k] = __fmul_rn(v[K + k], m[dgr]); v[2 * K + k] = __fmul_rn(v[2 * K + k], m[dgr]);
+    }
+  }
 }
 
 }  // namespace spf

@@ -305,25 +305,43 @@ SPF_HD void sh_eval_fused(int deg, float x, float y, float z, const float* sh, i
 // for every k:  b = B_k(x,y,z);  v = sum_c sh[k,c]*gm[c];  dsh[k,c] (+)= b*gm[c];  (gx,gy,gz) += v * dB_k/d(x,y,z).
 // Element (k,c) of sh / dsh lives at  k*sk + c*sc  (sk=3,sc=1 for [K,3]; sk=1,sc=Kstore for [3,K]).
 // dsh may alias sh (each element is read before it is written).  gm = dL/drgb with the clamp mask applied.
-template <bool ACCUM>
+// MASKED (raw-head input): sh holds the encoder's UNMASKED coefficients -- every read is multiplied by the degree's SH
+// mask (product rounded to fp32 first, like the masked tensor the stand-alone adapter stores), and without ACCUM the
+// gradient leaves already multiplied by the mask (d raw = d masked * mask); with ACCUM the caller applies the mask
+// once after the last view.
+#if defined(__CUDA_ARCH__)
+#define SPF_MUL_RN(a, b) __fmul_rn((a), (b))
+#else
+#define SPF_MUL_RN(a, b) ((a) * (b))
+#endif
+template <bool ACCUM, bool MASKED = false>
 SPF_HD void sh_backward_fused(int deg, float x, float y, float z, const float* sh, float* dsh, int sk, int sc,
                               const float gm[3], float& gx, float& gy, float& gz) {
   gx = gy = gz = 0.0f;
+  float mk = 1.0f;
 #define SPF_SH_TERM(k, B, DX, DY, DZ)                                                      \
   {                                                                                        \
     const float b_ = (B);                                                                  \
     const int i_ = (k) * sk;                                                               \
-    const float v_ = (sh[i_] * gm[0] + sh[i_ + sc] * gm[1]) + sh[i_ + 2 * sc] * gm[2];     \
+    const float s0_ = MASKED ? SPF_MUL_RN(sh[i_], mk) : sh[i_];                            \
+    const float s1_ = MASKED ? SPF_MUL_RN(sh[i_ + sc], mk) : sh[i_ + sc];                  \
+    const float s2_ = MASKED ? SPF_MUL_RN(sh[i_ + 2 * sc], mk) : sh[i_ + 2 * sc];          \
+    const float v_ = (s0_ * gm[0] + s1_ * gm[1]) + s2_ * gm[2];                            \
     if (ACCUM) { dsh[i_] += b_ * gm[0]; dsh[i_ + sc] += b_ * gm[1]; dsh[i_ + 2 * sc] += b_ * gm[2]; } \
-    else { dsh[i_] = b_ * gm[0]; dsh[i_ + sc] = b_ * gm[1]; dsh[i_ + 2 * sc] = b_ * gm[2]; } \
+    else if (MASKED) {                                                                     \
+      dsh[i_] = SPF_MUL_RN(SPF_MUL_RN(b_, gm[0]), mk); dsh[i_ + sc] = SPF_MUL_RN(SPF_MUL_RN(b_, gm[1]), mk); \
+      dsh[i_ + 2 * sc] = SPF_MUL_RN(SPF_MUL_RN(b_, gm[2]), mk);                            \
+    } else { dsh[i_] = b_ * gm[0]; dsh[i_ + sc] = b_ * gm[1]; dsh[i_ + 2 * sc] = b_ * gm[2]; } \
     gx += v_ * (DX); gy += v_ * (DY); gz += v_ * (DZ);                                     \
   }
   SPF_SH_TERM(0, SH_C0, 0.0f, 0.0f, 0.0f)
   if (deg < 1) return;
+  mk = SH_MASK_1;
   SPF_SH_TERM(1, -SH_C1 * y, 0.0f, -SH_C1, 0.0f)
   SPF_SH_TERM(2, SH_C1 * z, 0.0f, 0.0f, SH_C1)
   SPF_SH_TERM(3, -SH_C1 * x, -SH_C1, 0.0f, 0.0f)
   if (deg < 2) return;
+  mk = SH_MASK_2;
   const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
   SPF_SH_TERM(4, SH_C2_0 * xy, SH_C2_0 * y, SH_C2_0 * x, 0.0f)
   SPF_SH_TERM(5, SH_C2_1 * yz, 0.0f, SH_C2_1 * z, SH_C2_1 * y)
@@ -331,6 +349,7 @@ SPF_HD void sh_backward_fused(int deg, float x, float y, float z, const float* s
   SPF_SH_TERM(7, SH_C2_3 * xz, SH_C2_3 * z, 0.0f, SH_C2_3 * x)
   SPF_SH_TERM(8, SH_C2_4 * (xx - yy), SH_C2_4 * 2.0f * x, SH_C2_4 * -2.0f * y, 0.0f)
   if (deg < 3) return;
+  mk = SH_MASK_3;
   SPF_SH_TERM(9, SH_C3_0 * y * (3.0f * xx - yy), SH_C3_0 * 6.0f * xy, SH_C3_0 * 3.0f * (xx - yy), 0.0f)
   SPF_SH_TERM(10, SH_C3_1 * xy * z, SH_C3_1 * yz, SH_C3_1 * xz, SH_C3_1 * xy)
   SPF_SH_TERM(11, SH_C3_2 * y * (4.0f * zz - xx - yy), SH_C3_2 * -2.0f * xy, SH_C3_2 * (4.0f * zz - xx - 3.0f * yy),
@@ -342,6 +361,7 @@ SPF_HD void sh_backward_fused(int deg, float x, float y, float z, const float* s
   SPF_SH_TERM(14, SH_C3_5 * z * (xx - yy), SH_C3_5 * 2.0f * xz, SH_C3_5 * -2.0f * yz, SH_C3_5 * (xx - yy))
   SPF_SH_TERM(15, SH_C3_6 * x * (xx - 3.0f * yy), SH_C3_6 * 3.0f * (xx - yy), SH_C3_6 * -6.0f * xy, 0.0f)
   if (deg < 4) return;
+  mk = SH_MASK_4;
   SPF_SH_TERM(16, SH_C4_0 * xy * (xx - yy), SH_C4_0 * (3.0f * xx * y - yy * y), SH_C4_0 * (xx * x - 3.0f * x * yy), 0.0f)
   SPF_SH_TERM(17, SH_C4_1 * yz * (3.0f * xx - yy), SH_C4_1 * 6.0f * xy * z, SH_C4_1 * 3.0f * z * (xx - yy),
               SH_C4_1 * y * (3.0f * xx - yy))
@@ -359,6 +379,7 @@ SPF_HD void sh_backward_fused(int deg, float x, float y, float z, const float* s
   SPF_SH_TERM(24, SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy)), SH_C4_8 * 4.0f * x * (xx - 3.0f * yy),
               SH_C4_8 * 4.0f * y * (yy - 3.0f * xx), 0.0f)
 #undef SPF_SH_TERM
+  (void)mk;
 }
 
 // Upstream 2-D gradients of one Gaussian in one view (what blend-backward reduces).

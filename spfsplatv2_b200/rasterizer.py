@@ -559,11 +559,14 @@ def rasterize_batched_head(settings: RasterSettings, means: Tensor, head_out: Te
 
 
 def forward_with_state(settings: RasterSettings, means, scales, rotations, opacities, shs, colors, viewmatrix,
-                       projmatrix, tanfov, bg, pre_scale=None, pair_log: bool = False):
-    """No-autograd forward that also returns the intermediate state (for parity tests / profiling)."""
+                       projmatrix, tanfov, bg, pre_scale=None, pair_log: bool = False, raw=None):
+    """No-autograd forward that also returns the intermediate state (for parity tests / profiling).  ``raw`` =
+    (head rows, has_density, eps, opacity_exponent) selects the raw-head input (scales / rotations / shs then None)."""
     args = [None if a is None else _f32c(a.detach()) for a in
             (means, scales, rotations, opacities, shs, colors, viewmatrix, projmatrix, tanfov, bg, pre_scale)]
-    return _forward_impl(settings, *args, pair_log=pair_log)
+    if raw is not None:
+        raw = (_f32c(raw[0].detach()),) + tuple(raw[1:])
+    return _forward_impl(settings, *args, pair_log=pair_log, raw=raw)
 
 
 def unpack_sorted(st: _State):
@@ -582,14 +585,15 @@ BWD_STAGES = ("blend_backward", "project_backward", "pose_reduce")
 
 
 def profile_stages(settings: RasterSettings, means, scales, rotations, opacities, shs, colors, viewmatrix,
-                   projmatrix, tanfov, bg, pre_scale, g_color, g_depth, iters: int = 10) -> dict:
+                   projmatrix, tanfov, bg, pre_scale, g_color, g_depth, iters: int = 10, raw=None) -> dict:
     """Per-kernel device times (ms, mean over ``iters``) measured with CUDA events around each stage of
     the forward and backward launch sequences (spf_raster_{forward,backward}_stages), on the current
     stream.  Used by bench.py for the roofline of the dominant kernel."""
     lib = L.lib()
     color, depth, alpha, radii, st = forward_with_state(settings, means, scales, rotations, opacities, shs, colors,
-                                                        viewmatrix, projmatrix, tanfov, bg, pre_scale, pair_log=True)
+                                                        viewmatrix, projmatrix, tanfov, bg, pre_scale, pair_log=True, raw=raw)
     means_c, scales_c, rots_c, opac_c, shs_c, cols_c = st.keep[:6]
+    raw_c = st.keep[11] if len(st.keep) > 11 else None
     dev = means_c.device
     S, P = means_c.shape[0], means_c.shape[1]
     B = S * settings.views_per_scene
@@ -597,13 +601,13 @@ def profile_stages(settings: RasterSettings, means, scales, rotations, opacities
     f32 = dict(dtype=torch.float32, device=dev)
     gc, gd = _f32c(g_color), (None if g_depth is None else _f32c(g_depth))
     gout = L.SpfRasterGradOut(_ptr(gc), _ptr(gd), None)
+    e = lambda t: None if t is None else torch.empty_like(t)
     bufs = dict(dup_grad=torch.empty(max(st.n_dups, 1), 12, **f32), pose_partial=torch.empty(B, NB, 16, **f32),
-                d_means=torch.empty_like(means_c), d_scales=torch.empty_like(scales_c), d_rots=torch.empty_like(rots_c),
-                d_opac=torch.empty_like(opac_c), d_shs=None if shs_c is None else torch.empty_like(shs_c),
-                d_cols=None if cols_c is None else torch.empty_like(cols_c), d_view=torch.empty(B, 16, **f32))
+                d_means=e(means_c), d_scales=e(scales_c), d_rots=e(rots_c), d_opac=e(opac_c), d_shs=e(shs_c), d_cols=e(cols_c),
+                d_view=torch.empty(B, 16, **f32), d_raw=e(raw_c))
     gin = L.SpfRasterGradIn(_ptr(bufs["dup_grad"]), _ptr(bufs["pose_partial"]), _ptr(bufs["d_means"]),
                             _ptr(bufs["d_scales"]), _ptr(bufs["d_rots"]), _ptr(bufs["d_opac"]), _ptr(bufs["d_shs"]),
-                            _ptr(bufs["d_cols"]), _ptr(bufs["d_view"]), None)
+                            _ptr(bufs["d_cols"]), _ptr(bufs["d_view"]), None, _ptr(bufs["d_raw"]))
     cout = L.SpfRasterOut(_ptr(color), _ptr(depth), _ptr(alpha))
     stream = _stream(dev)
     cur = torch.cuda.current_stream(dev)
