@@ -8,6 +8,8 @@
 //
 // Replaces the preprocess stage of diff_gauss_pose (call site
 // /root/reference/src/model/decoder/cuda_splatting.py:128-138; algorithm SURVEY.md App. B 1-10).
+#include <cstdlib>
+
 #include "spf_adapter_math.cuh"
 #include "spf_device.cuh"
 #include "spf_kernels.h"
@@ -151,19 +153,24 @@ struct __align__(128) PFStage {
   float opac[PROJ_THREADS];
 };
 
-struct PFSmem {
-  PFStage stage[2];
+template <int NSTAGE>
+struct PFSmemT {
+  PFStage stage[NSTAGE];
   ViewConsts vc[VC_MAX];
   uint64_t full[2];
   int warp_tot[2][PROJ_THREADS / 32];
 };
 
-__global__ void __launch_bounds__(2 * PROJ_THREADS, 2)
+// NSTAGE = 2: two CTAs per SM, item k+1 in flight while item k is computed.  NSTAGE = 1: FOUR CTAs per SM, every CTA
+// loads, then computes -- the other three CTAs of the SM cover its load (twice the warps to hide the latency of the
+// dependent sqrt / divide / shared-memory chains of the compute phase).
+template <int NSTAGE>
+__global__ void __launch_bounds__(2 * PROJ_THREADS, NSTAGE == 1 ? 4 : 2)
 project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
                               int* __restrict__ block_sum) {
   pdl_enter();
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
-  PFSmem& S = *reinterpret_cast<PFSmem*>(pf_smem_raw);
+  PFSmemT<NSTAGE>& S = *reinterpret_cast<PFSmemT<NSTAGE>*>(pf_smem_raw);
   const int tid = threadIdx.x;
   const int row = 3 * in.sh_coeffs;
   const int total = d.B * d.NB;
@@ -195,17 +202,21 @@ project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __
   };
 
   int item = blockIdx.x;
-  if (tid == 0 && item < total) issue(item, 0);
+  if (NSTAGE == 2 && tid == 0 && item < total) issue(item, 0);
   for (int k = 0; item < total; ++k, item += gridDim.x) {
-    const int sidx = k & 1;
-    if (tid == 0 && item + (int)gridDim.x < total) issue(item + gridDim.x, sidx ^ 1);
+    const int sidx = NSTAGE == 2 ? (k & 1) : 0;
+    if (NSTAGE == 2) {
+      if (tid == 0 && item + (int)gridDim.x < total) issue(item + gridDim.x, sidx ^ 1);
+    } else if (tid == 0) {
+      issue(item, 0);      // the previous item's closing barrier has released the stage
+    }
     const int view = item / d.NB, chunk = item - view * d.NB;
     const int role = tid >> 7, gi = tid & (PROJ_THREADS - 1);   // warps 0-3: geometry, warps 4-7: SH colour
     const int g = chunk * PROJ_THREADS + gi;
     const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
     const ViewConsts& vc = S.vc[view];
     const PFStage& T = S.stage[sidx];
-    mbar_wait(&S.full[sidx], (uint32_t)((k >> 1) & 1));
+    mbar_wait(&S.full[sidx], (uint32_t)(NSTAGE == 2 ? ((k >> 1) & 1) : (k & 1)));
 
     int tiles = 0, cx0 = 0, cy0 = 0, cw = 1;
     const size_t vg = (size_t)view * d.P + g;
@@ -254,11 +265,11 @@ project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __
       }
     }
     const int wsum = warp_sum_i(tiles);
-    if (role == 0 && (tid & 31) == 0) S.warp_tot[sidx][tid >> 5] = wsum;
+    if (role == 0 && (tid & 31) == 0) S.warp_tot[k & 1][tid >> 5] = wsum;
     __syncthreads();     // stage sidx fully consumed (it is refilled two items later); warp totals visible
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < PROJ_THREADS / 32; ++w) t += S.warp_tot[sidx][w];
+      for (int w = 0; w < PROJ_THREADS / 32; ++w) t += S.warp_tot[k & 1][w];
       block_sum[(size_t)view * d.NB + chunk] = t;
     }
   }
@@ -277,19 +288,21 @@ struct __align__(128) PFRawStage {
   float opac[PROJ_THREADS];          // only when the rows carry no density logit
 };
 
-struct PFRawSmem {
-  PFRawStage stage[2];
+template <int NSTAGE>
+struct PFRawSmemT {
+  PFRawStage stage[NSTAGE];
   ViewConsts vc[VC_MAX];
   uint64_t full[2];
   int warp_tot[2][PROJ_THREADS / 32];
 };
 
-__global__ void __launch_bounds__(2 * PROJ_THREADS, 2)
+template <int NSTAGE>
+__global__ void __launch_bounds__(2 * PROJ_THREADS, NSTAGE == 1 ? 4 : 2)
 project_forward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restrict__ tile_count,
                            int* __restrict__ block_sum) {
   pdl_enter();
   extern __shared__ __align__(128) unsigned char pf_smem_raw[];
-  PFRawSmem& S = *reinterpret_cast<PFRawSmem*>(pf_smem_raw);
+  PFRawSmemT<NSTAGE>& S = *reinterpret_cast<PFRawSmemT<NSTAGE>*>(pf_smem_raw);
   const int tid = threadIdx.x;
   const int R = in.raw_stride, dens = in.raw_has_density ? 1 : 0;
   const int total = d.B * d.NB;
@@ -317,17 +330,21 @@ project_forward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __res
   };
 
   int item = blockIdx.x;
-  if (tid == 0 && item < total) issue(item, 0);
+  if (NSTAGE == 2 && tid == 0 && item < total) issue(item, 0);
   for (int k = 0; item < total; ++k, item += gridDim.x) {
-    const int sidx = k & 1;
-    if (tid == 0 && item + (int)gridDim.x < total) issue(item + gridDim.x, sidx ^ 1);
+    const int sidx = NSTAGE == 2 ? (k & 1) : 0;
+    if (NSTAGE == 2) {
+      if (tid == 0 && item + (int)gridDim.x < total) issue(item + gridDim.x, sidx ^ 1);
+    } else if (tid == 0) {
+      issue(item, 0);      // the previous item's closing barrier has released the stage
+    }
     const int view = item / d.NB, chunk = item - view * d.NB;
     const int role = tid >> 7, gi = tid & (PROJ_THREADS - 1);   // warps 0-3: geometry, warps 4-7: SH colour
     const int g = chunk * PROJ_THREADS + gi;
     const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
     const ViewConsts& vc = S.vc[view];
     const PFRawStage& T = S.stage[sidx];
-    mbar_wait(&S.full[sidx], (uint32_t)((k >> 1) & 1));
+    mbar_wait(&S.full[sidx], (uint32_t)(NSTAGE == 2 ? ((k >> 1) & 1) : (k & 1)));
     const float* rowp = T.raw + gi * R + dens;                  // [3 scale logits, 4 quaternion, 3 x K SH]
 
     int tiles = 0, cx0 = 0, cy0 = 0, cw = 1;
@@ -377,11 +394,11 @@ project_forward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __res
       }
     }
     const int wsum = warp_sum_i(tiles);
-    if (role == 0 && (tid & 31) == 0) S.warp_tot[sidx][tid >> 5] = wsum;
+    if (role == 0 && (tid & 31) == 0) S.warp_tot[k & 1][tid >> 5] = wsum;
     __syncthreads();     // stage sidx fully consumed (it is refilled two items later); warp totals visible
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < PROJ_THREADS / 32; ++w) t += S.warp_tot[sidx][w];
+      for (int w = 0; w < PROJ_THREADS / 32; ++w) t += S.warp_tot[k & 1][w];
       block_sum[(size_t)view * d.NB + chunk] = t;
     }
   }
@@ -400,13 +417,22 @@ static bool stream_ok(const Dims& d, const SpfRasterIn& in) {
 
 cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const SpfRasterState& st,
                                    const ControlLayout& cl, cudaStream_t s) {
+  // SPF_PF_STAGES=2 selects the two-stage ring at two CTAs per SM (A/B switch; default: one stage, four CTAs per SM)
+  static const bool two_stage = [] { const char* v = getenv("SPF_PF_STAGES"); return v && v[0] == '2'; }();
   if (in.raw_head) {      // (shape / alignment requirements were checked by the C entry point)
-    cudaError_t e = cudaFuncSetAttribute(project_forward_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(PFRawSmem));
+    if (two_stage) {
+      cudaError_t e = cudaFuncSetAttribute(project_forward_raw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(PFRawSmemT<2>));
+      if (e != cudaSuccess) return e;
+      pdl_launch(project_forward_raw_kernel<2>, min(d.B * d.NB, 2 * sm_count()), 2 * PROJ_THREADS, sizeof(PFRawSmemT<2>), s)(
+          d, in, st, st.control + cl.tile_count, st.control + cl.block_sum);
+      return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(project_forward_raw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PFRawSmemT<1>));
     if (e != cudaSuccess) return e;
-    const int grid1 = min(d.B * d.NB, 2 * sm_count());
-    pdl_launch(project_forward_raw_kernel, grid1, 2 * PROJ_THREADS, sizeof(PFRawSmem), s)(d, in, st, st.control + cl.tile_count,
-                                                                                  st.control + cl.block_sum);
+    pdl_launch(project_forward_raw_kernel<1>, min(d.B * d.NB, 4 * sm_count()), 2 * PROJ_THREADS, sizeof(PFRawSmemT<1>), s)(
+        d, in, st, st.control + cl.tile_count, st.control + cl.block_sum);
     return cudaGetLastError();
   }
   const int row = 3 * in.sh_coeffs;
@@ -418,12 +444,19 @@ cudaError_t launch_project_forward(const Dims& d, const SpfRasterIn& in, const S
     if (e != cudaSuccess) return e;
   }
   if (stream_ok(d, in) && !(d.flags & SPF_FLAG_NO_TMA)) {
-    cudaError_t e = cudaFuncSetAttribute(project_forward_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(PFSmem));
+    if (two_stage) {
+      cudaError_t e = cudaFuncSetAttribute(project_forward_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(PFSmemT<2>));
+      if (e != cudaSuccess) return e;
+      pdl_launch(project_forward_stream_kernel<2>, min(d.B * d.NB, 2 * sm_count()), 2 * PROJ_THREADS, sizeof(PFSmemT<2>), s)(
+          d, in, st, st.control + cl.tile_count, st.control + cl.block_sum);
+      return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(project_forward_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PFSmemT<1>));
     if (e != cudaSuccess) return e;
-    const int grid1 = min(d.B * d.NB, 2 * sm_count());
-    pdl_launch(project_forward_stream_kernel, grid1, 2 * PROJ_THREADS, sizeof(PFSmem), s)(d, in, st, st.control + cl.tile_count,
-                                                                             st.control + cl.block_sum);
+    pdl_launch(project_forward_stream_kernel<1>, min(d.B * d.NB, 4 * sm_count()), 2 * PROJ_THREADS, sizeof(PFSmemT<1>), s)(
+        d, in, st, st.control + cl.tile_count, st.control + cl.block_sum);
     return cudaGetLastError();
   }
   dim3 grid(d.NB, d.B);
