@@ -183,7 +183,31 @@ _wc_keepalive = []
 def _pin(t):
     """Page-locked copy of a host tensor.  SPF_PIN=wc allocates it write-combined (cudaHostAllocWriteCombined: the GPU's
     PCIe reads do not snoop the CPU caches) -- an A/B switch for the end-to-end loop; default: torch's pin_memory()."""
-    if os.environ.get("SPF_PIN", "") != "wc":
+    mode = os.environ.get("SPF_PIN", "")
+    if mode == "huge":
+        # 2 MiB-aligned anonymous mapping, MADV_HUGEPAGE, touched, then cudaHostRegister: with transparent huge pages
+        # the IOMMU walks 512x fewer entries per byte of DMA -- an A/B switch for the multi-rank end-to-end loop
+        import ctypes
+        import mmap
+        nbytes = max(t.numel() * t.element_size(), 1)
+        size = (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20)
+        mm = mmap.mmap(-1, size + (2 << 20), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+        off = (-base) % (2 << 20)
+        try:
+            mm.madvise(mmap.MADV_HUGEPAGE, off, size)
+        except Exception:
+            pass
+        buf = (ctypes.c_byte * nbytes).from_buffer(mm, off)
+        out = torch.frombuffer(buf, dtype=t.dtype, count=t.numel()).view(t.shape)
+        out.copy_(t)                                   # first touch: pages (huge if THP allows) are populated here
+        rt = ctypes.CDLL("libcudart.so.12")
+        rc = rt.cudaHostRegister(ctypes.c_void_p(base + off), ctypes.c_size_t(size), ctypes.c_uint(0))
+        if rc != 0:
+            return t.pin_memory()
+        _wc_keepalive.append((buf, mm))
+        return out
+    if mode != "wc":
         return t.pin_memory()
     import ctypes
     rt = ctypes.CDLL("libcudart.so.12")
