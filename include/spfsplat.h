@@ -236,6 +236,14 @@ SPF_API int spf_head_backward(const float* raw, const float* dL_dopacities, cons
                       const float* dL_dharmonics, int64_t n, int32_t sh_coeffs, float eps, float exponent, float* dL_draw,
                       void* stream);
 
+/* PLY vertex rows of a Gaussian scene, packed on the device.  Replaces the numpy / scipy body of export_ply
+ * (/root/reference/src/model/ply_export.py:76-141): rows [n,17] = x y z (R (mean - shift) / scale_factor), nx ny nz (0),
+ * f_dc_0..2 (the DC band of harmonics [n,3,sh_coeffs]), opacity (as stored), scale_0..2 (log(scale / scale_factor)),
+ * rot_0..3 ((w,x,y,z) of quat(R * matrix(q)), q given scalar-last like the reference's rotations).
+ * params (device, 13 floats) = R row-major (9), shift (3), scale_factor (1). */
+SPF_API int spf_ply_pack(const float* means, const float* scales, const float* rotations_xyzw, const float* harmonics,
+                 const float* opacities, const float* params, int64_t n, int32_t sh_coeffs, float* rows, void* stream);
+
 /* 2-D RoPE, in place.  Replaces rope_2d (curope.cpp:49-65).  tokens: [B,N,H,D] view with
  * stride(3)==1, stride(2)==D (kernels.cu:91); positions int64 [B,N,2] contiguous.
  * dtype: 0 = fp32, 1 = fp16, 2 = bf16, 3 = fp64 (the floating types the reference dispatches, kernels.cu:101, plus bf16;

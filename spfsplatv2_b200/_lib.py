@@ -57,7 +57,7 @@ class SpfRasterGradIn(C.Structure):
 EXPORTS = ("spf_version", "spf_last_error", "spf_raster_control_ints", "spf_raster_forward",
            "spf_raster_backward", "spf_raster_forward_stages", "spf_raster_backward_stages",
            "spf_raster_unpack_sorted", "spf_camera_forward", "spf_camera_backward", "spf_rope2d", "spf_rope2d_qk",
-           "spf_image_mse", "spf_image_mse_blocks", "spf_adapter_forward", "spf_adapter_backward", "spf_head_forward", "spf_head_backward",
+           "spf_image_mse", "spf_image_mse_blocks", "spf_adapter_forward", "spf_adapter_backward", "spf_head_forward", "spf_head_backward", "spf_ply_pack",
            "spf_multimem_allreduce_f32", "spf_multimem_allreduce_f32_fused")
 
 _lib = None
@@ -130,6 +130,8 @@ def lib() -> C.CDLL:
     l.spf_head_backward.restype = C.c_int
     l.spf_head_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                     C.c_float, C.c_void_p, C.c_void_p]
+    l.spf_ply_pack.restype = C.c_int
+    l.spf_ply_pack.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     l.spf_multimem_allreduce_f32.restype = C.c_int
     l.spf_multimem_allreduce_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     l.spf_multimem_allreduce_f32_fused.restype = C.c_int

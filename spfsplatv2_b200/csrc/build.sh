@@ -8,12 +8,12 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="-O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
 mkdir -p build
 pids=()
-for f in project_fwd binning blend project_bwd camera rope loss adapter allreduce capi; do
+for f in project_fwd binning blend project_bwd camera rope loss adapter ply allreduce capi; do
   EXTRA=""
   [ "$f" = project_fwd ] && EXTRA="-fmad=false"
   $NVCC $ARCH $FLAGS $EXTRA -c $f.cu -o build/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC $ARCH -shared -o ../libspfsplat.so build/project_fwd.o build/binning.o build/blend.o build/project_bwd.o build/camera.o build/rope.o build/loss.o build/adapter.o build/allreduce.o build/capi.o -lcudart
+$NVCC $ARCH -shared -o ../libspfsplat.so build/project_fwd.o build/binning.o build/blend.o build/project_bwd.o build/camera.o build/rope.o build/loss.o build/adapter.o build/ply.o build/allreduce.o build/capi.o -lcudart
 echo "built $(cd .. && pwd)/libspfsplat.so"

@@ -306,6 +306,17 @@ int spf_head_backward(const float* raw, const float* dL_dopacities, const float*
   return SPF_OK;
 }
 
+int spf_ply_pack(const float* means, const float* scales, const float* rotations_xyzw, const float* harmonics,
+                 const float* opacities, const float* params, int64_t n, int32_t sh_coeffs, float* rows, void* stream) {
+  if (!means || !scales || !rotations_xyzw || !harmonics || !opacities || !params || !rows)
+    return fail(SPF_ERR_BAD_ARG, "spf_ply_pack: NULL pointer");
+  if (n < 0 || sh_coeffs < 1) return fail(SPF_ERR_BAD_ARG, "spf_ply_pack: bad sizes");
+  cudaError_t e = spf::launch_ply_pack(means, scales, rotations_xyzw, harmonics, opacities, params, n, sh_coeffs, rows,
+                                       static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ply_pack");
+  return SPF_OK;
+}
+
 int spf_multimem_allreduce_f32(float* multicast_bucket, int64_t numel, int32_t rank, int32_t world, int32_t n_blocks,
                                void* stream) {
   if (!multicast_bucket) return fail(SPF_ERR_BAD_ARG, "spf_multimem_allreduce_f32: multicast address is NULL");

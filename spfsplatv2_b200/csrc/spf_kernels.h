@@ -123,6 +123,8 @@ cudaError_t launch_image_mse(const float* pred, const float* target, int n_image
 cudaError_t launch_multimem_allreduce_f32(float* mc, int64_t numel, int rank, int world, int n_blocks, cudaStream_t s);
 cudaError_t launch_multimem_allreduce_f32_fused(float* mc, int64_t numel, int rank, int world, int n_blocks,
                                                 uint32_t* const* signal_pads, int pad_word_offset, cudaStream_t s);
+cudaError_t launch_ply_pack(const float* means, const float* scales, const float* rots, const float* harmonics,
+                            const float* opac, const float* params, int64_t n, int sh_coeffs, float* out, cudaStream_t s);
 cudaError_t launch_adapter_forward(const float* raw, int64_t n, int K, float eps, int dens, float exponent, float* scales,
                                    float* rots, float* sh, float* opac, cudaStream_t s);
 cudaError_t launch_adapter_backward(const float* raw, const float* d_scales, const float* d_rots, const float* d_sh,

@@ -22,6 +22,7 @@ Fixtures
 """
 from __future__ import annotations
 
+import math
 import os
 import sys
 import types
@@ -307,6 +308,58 @@ def make_adapter():
     print(f"adapter: scales max {out.scales.max().item():.3f}, d_raw norm {raw.grad.norm().item():.3f}")
 
 
+def make_ply():
+    """The reference's export_ply (src/model/ply_export.py:76-141), unmodified, on a seeded scene; the absent `plyfile`
+    package is replaced by a recorder that keeps the element array the reference hands to PlyElement.describe (what
+    plyfile would serialise: 17 'f4' properties per vertex)."""
+    captured = {}
+    m = types.ModuleType("plyfile")
+
+    class PlyElement:
+        @staticmethod
+        def describe(elements, name):
+            captured["elements"], captured["name"] = elements, name
+            return ("element", name)
+
+    class PlyData:
+        def __init__(self, els):
+            self.els = els
+
+        def write(self, path):
+            captured["path"] = str(path)
+    m.PlyElement, m.PlyData = PlyElement, PlyData
+    sys.modules["plyfile"] = m
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    mod = importlib.import_module("src.model.ply_export")
+    g = torch.Generator().manual_seed(23)
+    n = 1500
+    means = torch.randn(n, 3, generator=g) * torch.tensor([2.0, 1.0, 4.0]) + torch.tensor([0.3, -0.2, 5.0])
+    scales = torch.exp(torch.randn(n, 3, generator=g) * 0.7 - 4.0)
+    rot = torch.randn(n, 4, generator=g)
+    rot = rot / rot.norm(dim=-1, keepdim=True)
+    rot[:4] = torch.tensor([[0.0, 0.0, 0.0, 1.0], [1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0]])   # all four pivots
+    harm = torch.randn(n, 3, 25, generator=g)
+    opac = torch.rand(n, generator=g)
+    a = 0.4
+    ext = torch.eye(4)
+    ext[:3, :3] = torch.tensor([[math.cos(a), 0.0, math.sin(a)], [0.0, 1.0, 0.0], [-math.sin(a), 0.0, math.cos(a)]]) @ \
+        torch.tensor([[1.0, 0.0, 0.0], [0.0, math.cos(0.2), -math.sin(0.2)], [0.0, math.sin(0.2), math.cos(0.2)]])
+    ext[:3, 3] = torch.tensor([0.5, 0.1, -0.3])
+    import tempfile
+    from pathlib import Path
+    mod.export_ply(ext, means, scales, rot, harm, opac, Path(tempfile.mkdtemp()) / "scene.ply")
+    el = captured["elements"]
+    names = list(el.dtype.names)
+    rows = np.stack([el[k] for k in names], axis=1).astype(np.float32)
+    assert names == mod.construct_list_of_attributes(0) and captured["name"] == "vertex" and rows.shape == (n, 17)
+    np.savez_compressed(os.path.join(HERE, "ply_ref.npz"), extrinsics=ext.numpy(), means=means.numpy(), scales=scales.numpy(),
+                        rotations=rot.numpy(), harmonics=harm.numpy(), opacities=opac.numpy(), rows=rows,
+                        names=np.array(names))
+    print(f"ply: {n} vertices, |xyz| 95% quantile {np.quantile(np.abs(rows[:, :3]), 0.95):.3f}")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("make_golden.py needs /root/reference (run it in the build container)")
@@ -314,6 +367,7 @@ if __name__ == "__main__":
     make_decoder()
     make_orthographic()
     make_adapter()
+    make_ply()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
