@@ -526,6 +526,7 @@ def run_ours(args):
             line["roofline_rope"] = rope_bench(dev, peaks["hbm_gbs"])
         if world == 1 and not args.no_head:
             line["head_path"] = head_path_bench(dec, dev_in, h, w, iters=max(10, args.steps))
+            line["level0_shim_loop"] = shim_loop_bench(sc, dev_in, h, w)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, sample_views=args.cpu_views)
         print(json.dumps(line), flush=True)
@@ -663,6 +664,42 @@ def head_path_bench(dec, dev_in, h, w, iters: int = 20) -> dict:
     res["note"] = ("head rows [b,P,83] -> image -> MSE -> d(head rows); unfused = spf_head_forward/backward + decoder, fused = "
                    "DecoderSplattingCUDA.forward_head (adapter + opacity mapping inside the projection kernels)")
     return res
+
+
+def shim_loop_bench(sc, dev_in, h, w, iters: int = 10) -> dict:
+    """INTEGRATION.md level 0, measured: the reference's per-view Python loop (cuda_splatting.py:96-143, restated in
+    tests/ref_probe.reference_render_loop) over this repo's drop-in ``diff_gauss_pose`` module -- one settings record and
+    one rasterizer call per view, eager PyTorch -- on the headline workload, next to the batched decoder that `value`
+    times.  What a maintainer gets with zero reference edits."""
+    from spfsplatv2_b200 import diff_gauss_pose as shim
+    from spfsplatv2_b200.loss import mse_loss
+    from tests.ref_probe import reference_render_loop
+    dev = dev_in["means"].device
+    b = dev_in["means"].shape[0]
+    names = ("means", "scales", "rotations", "opacities", "harmonics", "extrinsics")
+    bg = torch.zeros(b, 3, device=dev)
+
+    def step():
+        leaves = {k: dev_in[k].detach().requires_grad_() for k in names}
+        scd = sc.__class__(leaves["means"], None, leaves["rotations"], leaves["scales"], leaves["harmonics"], leaves["opacities"],
+                           leaves["extrinsics"], dev_in["intrinsics"], dev_in["near"], dev_in["far"], (h, w))
+        color, _ = reference_render_loop(shim, scd, bg, leaves=leaves)
+        loss = mse_loss(color, dev_in["gt"][:, 0])
+        loss.backward()
+        return loss
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / iters
+    return {"ms_per_step": round(ms, 3), "views_per_s": round(b / (ms * 1e-3), 1), "rasterizer_calls_per_step": b,
+            "note": "reference per-view loop (cuda_splatting.py:96-143) over spfsplatv2_b200.diff_gauss_pose, eager, host-bound"}
 
 
 def cpu_baseline(workload: str, sample_views: int = 3) -> dict:
