@@ -82,3 +82,41 @@ def reference_render_loop(mod, sc, background, use_sh: bool = True, enable_cov_g
     color = torch.stack(images)
     depth = torch.stack(depths).reshape(b * v, 1, h, w) * sc.near.reshape(-1).to(dev)[:, None, None, None]
     return color, depth
+
+
+def reference_tree():
+    """Path of the unmodified reference python tree under baseline/_ref (put there by __graft_entry__.build() in the
+    build container), or None."""
+    d = os.path.join(ROOT, "baseline", "_ref")
+    return d if os.path.isfile(os.path.join(d, "src", "model", "decoder", "cuda_splatting.py")) else None
+
+
+def stub_absent_third_party_modules():
+    """The reference's decoder package imports (transitively) a dozen third-party modules this image does not have
+    (dacite, lightning, skvideo, ...); none of them is touched on the decoder path.  Absent ones are
+    replaced by permissive placeholders, present ones are left alone -- as tests/golden/make_golden.py does."""
+    import types
+    import torchvision  # noqa: F401  (the real one first)
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            t = type(name, (), {"__init__": lambda self, *a, **k: None})
+            setattr(self, name, t)
+            return t
+
+    for name in ("dacite", "lightning", "lightning.pytorch", "skvideo", "skvideo.io", "matplotlib",
+                 "matplotlib.figure", "omegaconf", "pytorch3d", "pytorch3d.transforms", "lightning.pytorch.loggers",
+                 "lightning.pytorch.loggers.wandb", "lightning.pytorch.utilities", "lightning.pytorch.callbacks",
+                 "lightning.pytorch.plugins.environments", "lightning.pytorch.plugins", "matplotlib.pyplot",
+                 "matplotlib.cm", "matplotlib.colors", "lpips", "plyfile", "wandb", "colorspacious", "moviepy",
+                 "moviepy.editor", "hydra", "skimage", "skimage.metrics", "roma", "e3nn", "e3nn.o3", "timm", "timm.models",
+                 "timm.models.layers", "timm.layers", "huggingface_hub", "safetensors", "safetensors.torch", "xformers", "xformers.ops"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                m = _Any(name)
+                m.__path__ = []
+                sys.modules[name] = m
