@@ -422,6 +422,7 @@ class _Rasterize(torch.autograd.Function):
         ctx.shapes = (means.shape, scales.shape, rots.shape, opac.shape,
                       None if shs is None else shs.shape, None if colors is None else colors.shape,
                       viewmat.shape, None if means2d is None else means2d.shape)
+        ctx.dtypes = tuple(None if t is None else t.dtype for t in (means, scales, rots, opac, shs, colors, viewmat, means2d))
         ctx.mark_non_differentiable(radii)
         if alpha is None:
             alpha = torch.empty(0, device=color.device)
@@ -432,9 +433,10 @@ class _Rasterize(torch.autograd.Function):
     def backward(ctx, g_color, g_depth, g_alpha, _g_radii):
         sh = ctx.shapes
         g = _backward_impl(ctx.st, ctx.settings, g_color, g_depth, g_alpha, want_m2d=sh[7] is not None)
-        v = lambda t, shape: None if t is None else t.view(shape)
-        return (None, v(g["means"], sh[0]), v(g["scales"], sh[1]), v(g["rots"], sh[2]), v(g["opac"], sh[3]),
-                v(g["shs"], sh[4]), v(g["cols"], sh[5]), v(g["view"], sh[6]), None, None, None, None, v(g["m2d"], sh[7]))
+        dt = ctx.dtypes      # gradients are computed in fp32; handed back in each input's own dtype (a no-op for fp32 inputs)
+        v = lambda t, i: None if t is None else t.view(sh[i]).to(dt[i])
+        return (None, v(g["means"], 0), v(g["scales"], 1), v(g["rots"], 2), v(g["opac"], 3), v(g["shs"], 4), v(g["cols"], 5),
+                v(g["view"], 6), None, None, None, None, v(g["m2d"], 7))
 
 
 def _backward_impl(st: "_State", s: RasterSettings, g_color, g_depth, g_alpha, want_m2d: bool) -> dict:
@@ -498,6 +500,7 @@ class _RasterizeHead(torch.autograd.Function):
         ctx.settings, ctx.st = settings, st
         ctx.shapes = (means.shape, head.shape, None if opac is None else opac.shape, viewmat.shape,
                       None if means2d is None else means2d.shape)
+        ctx.dtypes = tuple(None if t is None else t.dtype for t in (means, head, opac, viewmat, means2d))
         ctx.mark_non_differentiable(radii)
         if alpha is None:
             alpha = torch.empty(0, device=color.device)
@@ -508,9 +511,10 @@ class _RasterizeHead(torch.autograd.Function):
     def backward(ctx, g_color, g_depth, g_alpha, _g_radii):
         sh = ctx.shapes
         g = _backward_impl(ctx.st, ctx.settings, g_color, g_depth, g_alpha, want_m2d=sh[4] is not None)
-        v = lambda t, shape: None if t is None else t.view(shape)
-        return (None, v(g["means"], sh[0]), v(g["raw"], sh[1]), v(g["opac"], sh[2]), v(g["view"], sh[3]), None, None, None,
-                None, v(g["m2d"], sh[4]), None, None)
+        dt = ctx.dtypes
+        v = lambda t, i: None if t is None else t.view(sh[i]).to(dt[i])
+        return (None, v(g["means"], 0), v(g["raw"], 1), v(g["opac"], 2), v(g["view"], 3), None, None, None, None, v(g["m2d"], 4),
+                None, None)
 
 
 _last_state = [None]

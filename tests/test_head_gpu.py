@@ -99,3 +99,24 @@ def test_raw_head_with_separate_opacities_and_errors():
         rasterize_batched_head(RasterSettings(64, 64, 4), sc.means[:, :1023], head[:, :1023].contiguous(), view, proj, tanfov, bg)
     with pytest.raises(ValueError):       # row width does not match the SH degree
         rasterize_batched_head(RasterSettings(64, 64, 4), sc.means, head[..., :80].contiguous(), view, proj, tanfov, bg)
+
+
+def test_half_precision_inputs_get_gradients_in_their_own_dtype():
+    """bf16 head rows / Gaussian tensors (an autocast encoder) are widened to fp32 on the way in; the gradients come back
+    in the input's dtype, as autograd requires."""
+    from spfsplatv2_b200.camera import camera_setup_cuda
+    from spfsplatv2_b200.rasterizer import RasterSettings, rasterize_batched, rasterize_batched_head
+    sc, head = _inputs(9, 1, 1, 32, 32, 64, 64)
+    view, proj, tanfov, scale = camera_setup_cuda(sc.extrinsics.reshape(1, 4, 4), sc.intrinsics.reshape(1, 3, 3),
+                                                  sc.near.reshape(1), sc.far.reshape(1), True)
+    bg = torch.zeros(1, 3, device=D0)
+    h = head.to(torch.bfloat16).requires_grad_()
+    c, d, _, _ = rasterize_batched_head(RasterSettings(64, 64, 4), sc.means, h, view, proj, tanfov, bg, scale)
+    c.square().sum().backward()
+    assert h.grad.dtype == torch.bfloat16 and torch.isfinite(h.grad.float()).all() and h.grad.float().abs().max().item() > 0
+    m = sc.means.to(torch.float64).requires_grad_()
+    sh = sc.harmonics.to(torch.float16).requires_grad_()
+    c2, _, _, _ = rasterize_batched(RasterSettings(64, 64, 4, sh_layout_ck=True), m, sc.scales, sc.rotations, sc.opacities, sh, None,
+                                    view, proj, tanfov, bg, scale)
+    c2.sum().backward()
+    assert m.grad.dtype == torch.float64 and sh.grad.dtype == torch.float16
