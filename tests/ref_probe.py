@@ -85,8 +85,8 @@ def reference_render_loop(mod, sc, background, use_sh: bool = True, enable_cov_g
 
 
 def reference_tree():
-    """Path of the unmodified reference python tree under baseline/_ref (put there by __graft_entry__.build() in the
-    build container), or None."""
+    """Path of an unmodified copy of the reference's python tree under baseline/_ref (placed there by whoever runs the
+    test: `cp -r /root/reference/src baseline/_ref/src`; never shipped with the repo), or None."""
     d = os.path.join(ROOT, "baseline", "_ref")
     return d if os.path.isfile(os.path.join(d, "src", "model", "decoder", "cuda_splatting.py")) else None
 

@@ -1,9 +1,13 @@
 """The reference's OWN decoder code, unmodified, on top of this repo's drop-in rasterizer, on a GPU (SURVEY.md 8b:
-integration level 0).  baseline/_ref/src is a verbatim copy of /root/reference/src made by __graft_entry__.build() in the
-build container (git-ignored; it travels to the GPU box with the snapshot); the only thing changed is what
-``import diff_gauss_pose`` resolves to (spfsplatv2_b200.install_shims, as INTEGRATION.md tells a maintainer to do).
-Checked against (a) the fixture the same reference code produced on the CPU oracle (tests/golden/decoder_ref.npz) and
-(b) this repo's batched DecoderSplattingCUDA on the same inputs."""
+integration level 0).  Needs a verbatim copy of the reference's `src` package at baseline/_ref/src (git-ignored; where
+the base contract puts an installed reference) -- SPFSplatV2 is not pip-installable, so that is `cp -r
+/root/reference/src baseline/_ref/src`.  The tree is NOT shipped with the repo (reference sources are never copied into
+it): without it the tests skip and say so.  It was run once this round with the tree placed there by hand for that one
+GPU call (profiles/r2_ref_decoder_on_dropin.log: both tests passed; sha256 of the two decoder files equal to
+/root/reference's).  The only thing changed is what ``import diff_gauss_pose`` resolves to
+(spfsplatv2_b200.install_shims, as INTEGRATION.md tells a maintainer to do).  Checked against (a) the fixture the same
+reference code produced on the CPU oracle (tests/golden/decoder_ref.npz) and (b) this repo's batched
+DecoderSplattingCUDA on the same inputs."""
 import os
 import sys
 
@@ -20,8 +24,8 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 def _reference_decoder_modules():
     tree = reference_tree()
     if tree is None:
-        pytest.skip("baseline/_ref/src is absent (the unmodified reference tree is copied there by __graft_entry__.build() "
-                    "where /root/reference exists)")
+        pytest.skip("baseline/_ref/src is absent (a verbatim copy of the reference's src package; never shipped with this "
+                    "repo -- see the module docstring and profiles/r2_ref_decoder_on_dropin.log)")
     import spfsplatv2_b200
     stub_absent_third_party_modules()
     spfsplatv2_b200.install_shims()
