@@ -120,3 +120,26 @@ def test_half_precision_inputs_get_gradients_in_their_own_dtype():
                                     view, proj, tanfov, bg, scale)
     c2.sum().backward()
     assert m.grad.dtype == torch.float64 and sh.grad.dtype == torch.float16
+
+
+def test_raw_head_with_a_lower_sh_degree():
+    """Degree-2 harmonics (9 coefficients, rows of 1 + 7 + 27): the row stride, the SH mask and the bulk-copy sizes all
+    depend on it."""
+    from spfsplatv2_b200.adapter import GaussianAdapterCfg, UnifiedGaussianAdapter
+    from spfsplatv2_b200.synthetic import make_batch
+    sc = make_batch(2, seed=13, v_cxt=1, h=64, w=64, grid=(36, 36), regime="init", n_target=2, d_sh=9).to(D0)
+    g = torch.Generator().manual_seed(5)
+    head = torch.randn(2, sc.means.shape[1], 1 + 7 + 27, generator=g)
+    head[..., 1:4] = head[..., 1:4] * 2.0 + 4.0
+    head = head.to(D0)
+    dec = _decoder()
+    ad = UnifiedGaussianAdapter(GaussianAdapterCfg(0.5, 15.0, 2))
+    h0, h1 = head.clone().requires_grad_(), head.clone().requires_grad_()
+    o0 = dec(ad.forward_head(sc.means, h0), sc.extrinsics, sc.intrinsics, sc.near, sc.far, sc.image_shape)
+    o1 = dec.forward_head(sc.means, h1, sc.extrinsics, sc.intrinsics, sc.near, sc.far, sc.image_shape, sh_degree=2)
+    assert torch.equal(o0.color, o1.color) and torch.equal(o0.depth, o1.depth) and o0.color.abs().max().item() > 0.3
+    wc = torch.randn_like(o0.color)
+    (o0.color * wc).sum().backward()
+    (o1.color * wc).sum().backward()
+    rel = ((h1.grad.double() - h0.grad.double()).norm() / h0.grad.double().norm()).item()
+    assert rel < 1e-6
