@@ -92,7 +92,7 @@ typedef struct {
    * 4 quaternion components, 3 x sh_coeffs SH coefficients ([3][K], the encoder's layout)], mapped inside the kernels
    * exactly like UnifiedGaussianAdapter (gaussian_adapter.py:122-150) and EncoderSPFSplatV2.map_pdf_to_opacity
    * (encoder_spfsplatv2.py:146-159,255-268).  Neither the adapter's outputs nor their gradients ever exist in HBM.
-   * Requires n_gaussians % 4 == 0, 16-byte aligned tensors, at most 32 views per call. */
+   * Requires n_gaussians % 4 == 0 and 16-byte aligned tensors. */
   const float* raw_head;     /* [S,P,raw_stride] or NULL */
   int32_t      raw_stride;   /* floats per row = raw_has_density + 7 + 3*sh_coeffs */
   int32_t      raw_has_density;

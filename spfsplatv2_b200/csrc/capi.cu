@@ -88,8 +88,8 @@ int check_in(const SpfRasterDesc* desc, const SpfRasterIn* in) {
     if (in->raw_stride != (in->raw_has_density ? 1 : 0) + 7 + 3 * in->sh_coeffs)
       return fail(SPF_ERR_BAD_ARG, "raw_stride must be raw_has_density + 7 + 3 * sh_coeffs");
     if (!(in->opacity_exponent > 0.0f)) return fail(SPF_ERR_BAD_ARG, "opacity_exponent must be positive");
-    if (desc->n_gaussians % 4 != 0 || (int64_t)desc->n_scenes * desc->views_per_scene > 32)
-      return fail(SPF_ERR_UNSUPPORTED, "raw_head needs n_gaussians % 4 == 0 and at most 32 views per call");
+    if (desc->n_gaussians % 4 != 0)
+      return fail(SPF_ERR_UNSUPPORTED, "raw_head needs n_gaussians % 4 == 0 (16-byte aligned rows for the bulk copies)");
     if ((reinterpret_cast<uintptr_t>(in->raw_head) | reinterpret_cast<uintptr_t>(in->means3D) |
          reinterpret_cast<uintptr_t>(in->opacities)) & 15)
       return fail(SPF_ERR_BAD_ARG, "raw_head / means3D / opacities must be 16-byte aligned");

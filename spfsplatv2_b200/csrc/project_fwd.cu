@@ -136,13 +136,21 @@ project_forward_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Streaming variant (the common case: SH colours, odd row length, 16-byte aligned tensors, P % 4 == 0, B <= VC_MAX):
+// Streaming variant (the common case: SH colours, odd row length, 16-byte aligned tensors, P % 4 == 0):
 // a PERSISTENT kernel, two CTAs per SM, each looping over (view, 128-Gaussian chunk) items with a two-stage
 // shared-memory ring.  ALL inputs of an item (SH rows 38.4 KB, means, scales, rotations, opacities) are moved by 1-D
 // TMA bulk copies onto one mbarrier, and the copies of item k+1 are issued before item k is computed: the memory
 // system always has a full chunk per CTA in flight, while the one-shot kernel above only loads during the first
 // part of every block's life (ncu: 50 % of HBM peak, long-scoreboard + barrier stalls).  Same arithmetic, same
 // op order (same functions, same -fmad=false translation unit) => same bits.
+// Per-view constants of item `view` (thread-serial: 32 cached loads and a handful of flops).
+__device__ __forceinline__ void load_view_consts(ViewConsts& vc, const Dims& d, const SpfRasterIn& in, int view) {
+  float V[16], Pm[16], bg[3];
+  for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[view * 16 + i]; Pm[i] = in.projmatrix[view * 16 + i]; }
+  for (int i = 0; i < 3; ++i) bg[i] = in.bg[view * 3 + i];
+  make_view_consts(vc, V, Pm, in.tanfov[view * 2], in.tanfov[view * 2 + 1], bg, d.mod, d.W, d.H);
+}
+
 constexpr int VC_MAX = 32;
 
 struct __align__(128) PFStage {
@@ -178,11 +186,15 @@ project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __
   const int sk = ck ? 1 : 3, sc = ck ? in.sh_coeffs : 1;
 
   if (tid == 0) { mbar_init(&S.full[0], 1); mbar_init(&S.full[1], 1); mbar_fence_init(); }
-  if (tid < d.B) {
-    float V[16], Pm[16], bg[3];
-    for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[tid * 16 + i]; Pm[i] = in.projmatrix[tid * 16 + i]; }
-    for (int i = 0; i < 3; ++i) bg[i] = in.bg[tid * 3 + i];
-    make_view_consts(S.vc[tid], V, Pm, in.tanfov[tid * 2], in.tanfov[tid * 2 + 1], bg, d.mod, d.W, d.H);
+  // Up to VC_MAX views: every view's constants are built once into a table.  More views (validation / video renders with
+  // hundreds of views per scene): the table is a two-entry ring, the constants of item k+1 are built by the block's last
+  // thread while item k is computed (published by item k's closing barrier).
+  const bool per_item = d.B > VC_MAX;
+  const int vc_thread = 2 * PROJ_THREADS - 1;
+  if (!per_item) {
+    if (tid < d.B) load_view_consts(S.vc[tid], d, in, tid);
+  } else if (tid == vc_thread && (int)blockIdx.x < total) {
+    load_view_consts(S.vc[0], d, in, (int)blockIdx.x / d.NB);
   }
   __syncthreads();
 
@@ -214,7 +226,9 @@ project_forward_stream_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __
     const int role = tid >> 7, gi = tid & (PROJ_THREADS - 1);   // warps 0-3: geometry, warps 4-7: SH colour
     const int g = chunk * PROJ_THREADS + gi;
     const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
-    const ViewConsts& vc = S.vc[view];
+    if (per_item && tid == vc_thread && item + (int)gridDim.x < total)
+      load_view_consts(S.vc[(k + 1) & 1], d, in, (item + (int)gridDim.x) / d.NB);
+    const ViewConsts& vc = S.vc[per_item ? (k & 1) : view];
     const PFStage& T = S.stage[sidx];
     mbar_wait(&S.full[sidx], (uint32_t)(NSTAGE == 2 ? ((k >> 1) & 1) : (k & 1)));
 
@@ -308,11 +322,15 @@ project_forward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __res
   const int total = d.B * d.NB;
 
   if (tid == 0) { mbar_init(&S.full[0], 1); mbar_init(&S.full[1], 1); mbar_fence_init(); }
-  if (tid < d.B) {
-    float V[16], Pm[16], bg[3];
-    for (int i = 0; i < 16; ++i) { V[i] = in.viewmatrix[tid * 16 + i]; Pm[i] = in.projmatrix[tid * 16 + i]; }
-    for (int i = 0; i < 3; ++i) bg[i] = in.bg[tid * 3 + i];
-    make_view_consts(S.vc[tid], V, Pm, in.tanfov[tid * 2], in.tanfov[tid * 2 + 1], bg, d.mod, d.W, d.H);
+  // Up to VC_MAX views: every view's constants are built once into a table.  More views (validation / video renders with
+  // hundreds of views per scene): the table is a two-entry ring, the constants of item k+1 are built by the block's last
+  // thread while item k is computed (published by item k's closing barrier).
+  const bool per_item = d.B > VC_MAX;
+  const int vc_thread = 2 * PROJ_THREADS - 1;
+  if (!per_item) {
+    if (tid < d.B) load_view_consts(S.vc[tid], d, in, tid);
+  } else if (tid == vc_thread && (int)blockIdx.x < total) {
+    load_view_consts(S.vc[0], d, in, (int)blockIdx.x / d.NB);
   }
   __syncthreads();
 
@@ -342,7 +360,9 @@ project_forward_raw_kernel(Dims d, SpfRasterIn in, SpfRasterState st, int* __res
     const int role = tid >> 7, gi = tid & (PROJ_THREADS - 1);   // warps 0-3: geometry, warps 4-7: SH colour
     const int g = chunk * PROJ_THREADS + gi;
     const float ps = in.pre_scale ? __ldg(in.pre_scale + view) : 1.0f;
-    const ViewConsts& vc = S.vc[view];
+    if (per_item && tid == vc_thread && item + (int)gridDim.x < total)
+      load_view_consts(S.vc[(k + 1) & 1], d, in, (item + (int)gridDim.x) / d.NB);
+    const ViewConsts& vc = S.vc[per_item ? (k & 1) : view];
     const PFRawStage& T = S.stage[sidx];
     mbar_wait(&S.full[sidx], (uint32_t)(NSTAGE == 2 ? ((k >> 1) & 1) : (k & 1)));
     const float* rowp = T.raw + gi * R + dens;                  // [3 scale logits, 4 quaternion, 3 x K SH]
@@ -408,7 +428,7 @@ static bool stream_ok(const Dims& d, const SpfRasterIn& in) {
   if (!in.shs) return false;
   const int row = 3 * in.sh_coeffs;
   if (!(row & 1) || row > 75) return false;
-  if (d.P % 4 != 0 || d.B > VC_MAX) return false;
+  if (d.P % 4 != 0) return false;
   const uintptr_t a = reinterpret_cast<uintptr_t>(in.shs) | reinterpret_cast<uintptr_t>(in.means3D) |
                       reinterpret_cast<uintptr_t>(in.scales) | reinterpret_cast<uintptr_t>(in.rotations) |
                       reinterpret_cast<uintptr_t>(in.opacities);

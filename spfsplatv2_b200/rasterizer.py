@@ -557,7 +557,7 @@ def rasterize_batched_head(settings: RasterSettings, means: Tensor, head_out: Te
     adapter's own contract).  The adapter's maps and the opacity mapping (gaussian_adapter.py:122-150,
     encoder_spfsplatv2.py:146-159,255-268) run inside the projection kernels; scales / rotations / harmonics / opacities
     and their gradients never exist in HBM.  Same outputs as ``rasterize_batched``; differentiable wrt means, head_out,
-    opacities and viewmatrix.  Needs P % 4 == 0 and at most 32 views per call."""
+    opacities and viewmatrix.  Needs P % 4 == 0."""
     return _RasterizeHead.apply(settings, means, head_out, opacities, viewmatrix, projmatrix, tanfov, bg, pre_scale,
                                 means2d, float(eps), float(opacity_exponent))
 

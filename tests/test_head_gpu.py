@@ -35,7 +35,7 @@ def _loss(o, wc, wd):
 
 
 @pytest.mark.parametrize("b,v,exponent,flags", [(2, 1, 1.0, (True, True)), (1, 3, 2 ** 1.5, (True, True)),
-                                                (2, 2, 1.0, (False, False))])
+                                                (2, 2, 1.0, (False, False)), (1, 36, 1.0, (True, True))])   # 36 > the camera table
 def test_raw_head_matches_adapter_then_decoder(b, v, exponent, flags):
     from spfsplatv2_b200.adapter import GaussianAdapterCfg, OpacityMappingCfg, UnifiedGaussianAdapter
     sc, head = _inputs(3, b, v, 48, 48, 96, 96)

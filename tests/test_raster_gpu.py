@@ -684,6 +684,27 @@ def test_odd_sizes_and_many_views_take_the_fallback_paths():
     assert rel_err(ext.grad, leaves["extrinsics"].grad) < GRAD_TOL
 
 
+def test_many_views_on_the_streaming_projection_kernels():
+    """More views than the per-CTA camera table holds (validation / video renders: up to 300 views of a scene) with
+    shapes the TMA-streamed projection kernels accept: the view constants are then built per item.  Parity bars against
+    the oracle on a few views, gradients summed over all 40."""
+    d = _dev()
+    sc = make_scene(seed=61, v_cxt=1, h=48, w=48, grid=(32, 32), regime="trained", n_target=40)    # P = 1024
+    assert sc.means.shape[1] % 4 == 0
+    ref, leaves = oracle_views(sc, bg=(0.2, 0.1, 0.3), requires_grad=True)
+    wc = torch.randn(40, 3, 48, 48, generator=torch.Generator().manual_seed(6))
+    loss = sum((r["color"] * wc[i]).sum() for i, r in enumerate(ref))
+    loss.backward()
+    color, depth, t, ext = _cuda_render_identical_inputs(sc, (0.2, 0.1, 0.3))
+    for i in (0, 21, 33, 39):
+        assert (color[i].cpu() - ref[i]["color"]).abs().max().item() < 3e-5
+    (color * wc.to(d)).sum().backward()
+    for name in ("means", "scales", "rotations", "opacities", "harmonics"):
+        e = rel_err(t[name].grad.cpu(), leaves[name].grad)
+        assert e < GRAD_TOL, f"{name}: rel err {e:.3e}"
+    assert rel_err(ext.grad, leaves["extrinsics"].grad) < GRAD_TOL
+
+
 def test_pose_align_graph_matches_the_eager_loop():
     """spfsplatv2_b200.pose_align.pose_align (the reference's test-time pose refinement, model_wrapper.py:539-590, as one
     captured CUDA graph per iteration) reproduces the plain eager loop -- decoder forward, MSE, backward, Adam on the
