@@ -527,6 +527,7 @@ def run_ours(args):
         if world == 1 and not args.no_head:
             line["head_path"] = head_path_bench(dec, dev_in, h, w, iters=max(10, args.steps))
             line["level0_shim_loop"] = shim_loop_bench(sc, dev_in, h, w)
+            line["video_render"] = video_render_bench(dec, h, w)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload, sample_views=args.cpu_views)
         print(json.dumps(line), flush=True)
@@ -700,6 +701,40 @@ def shim_loop_bench(sc, dev_in, h, w, iters: int = 10) -> dict:
     ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / iters
     return {"ms_per_step": round(ms, 3), "views_per_s": round(b / (ms * 1e-3), 1), "rasterizer_calls_per_step": b,
             "note": "reference per-view loop (cuda_splatting.py:96-143) over spfsplatv2_b200.diff_gauss_pose, eager, host-bound"}
+
+
+def video_render_bench(dec, h, w, n_views: int = 128, iters: int = 5) -> dict:
+    """Validation / video rendering (model_wrapper.py:941-956: up to 300 views of ONE scene, no gradients): the reference
+    repeats every Gaussian tensor per view (decoder_splatting_cuda.py:58-64, 39 MB of SH per view at P = 131 072) and
+    loops; here `n_views` cameras on a circle around a re10k 2-view scene go through ONE launch sequence, view i reading
+    the scene's single copy.  Device-timed, eager."""
+    import math
+    from spfsplatv2_b200.decoder import Gaussians
+    from spfsplatv2_b200.synthetic import make_scene
+    dev = next(dec.buffers()).device
+    sc = make_scene(seed=7, v_cxt=2, h=h, w=w, regime="init", n_target=1).to(dev)
+    ext = sc.extrinsics[:, :1].repeat(1, n_views, 1, 1).clone()
+    for i in range(n_views):
+        a = 2 * math.pi * i / n_views
+        ext[0, i, 0, 3] = 0.5 + 0.15 * math.cos(a)
+        ext[0, i, 1, 3] = 0.05 + 0.15 * math.sin(a)
+    rep = lambda t: t[:, :1].repeat(1, n_views, *([1] * (t.dim() - 2)))
+    G = Gaussians(sc.means, sc.covariances, sc.rotations, sc.scales, sc.harmonics, sc.opacities)
+    args = (G, ext, rep(sc.intrinsics), rep(sc.near), rep(sc.far), (h, w))
+    with torch.no_grad():
+        for _ in range(2):
+            out = dec(*args)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = dec(*args)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    return {"views": n_views, "gaussians": int(sc.means.shape[1]), "ms_per_call": round(ms, 3),
+            "views_per_s": round(n_views / (ms * 1e-3), 1), "finite": bool(torch.isfinite(out.color).all()),
+            "note": "forward only, one scene, all views in one call (views_per_scene index math, no repeat copies)"}
 
 
 def cpu_baseline(workload: str, sample_views: int = 3) -> dict:
